@@ -1,0 +1,943 @@
+// api.cu — the extern "C" layer of lib2dtissue_b200.so (include/t2d.h) and the host-side engine behind it.
+//
+// One context = one GPU = one CUDA stream.  The context owns all device memory: chart (UV triangles, 3-D
+// vertices, UV grid), thresholded CSR of the vertex-distance table, cos/sin table, particle SoA (double
+// buffered for the counting sort) and the staging areas for the reference-layout host arrays.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "io_kernels.cuh"
+#include "t2d_internal.h"
+
+namespace t2d {
+int launch_hop_table(int V, const int* d_adj_start, const int* d_adj, uint8_t* out_dev, int sm_count, cudaStream_t s);
+}
+
+using namespace t2d;
+
+static std::string g_create_error;
+
+namespace {
+
+struct CudaError {
+    std::string msg;
+};
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            char b__[512];                                                                                   \
+            snprintf(b__, sizeof(b__), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            throw CudaError{b__};                                                                            \
+        }                                                                                                    \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc((void**)&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T>& h, cudaStream_t s)
+    {
+        alloc(h.size());
+        if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+struct EngineBase {
+    virtual ~EngineBase() {}
+    virtual int set_state(int N, const double* uv, const int* heading, const int* vid, const double* r3d,
+                          const uint32_t* ids, bool project) = 0;
+    virtual int download(double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, int* face) = 0;
+    virtual int step(int nsteps) = 0;
+    virtual int step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color) = 0;
+    virtual int observables(double* out) = 0;
+    virtual int get_counters(t2d_counters* out) = 0;
+    virtual int reset_counters() = 0;
+    virtual int set_params(const t2d_params* p) = 0;
+    virtual int get_r3d(int N, const double* uv, double* r3d, int* vid, int* face) = 0;
+    virtual int tiling(int N, double* uv_old, double* uv, int* heading) = 0;
+    virtual int unit_vectors(int N, const int* heading, double* out) = 0;
+    virtual int forces(double* F, int* new_heading, int* color) = 0;
+    virtual int hop_table(uint8_t* out) = 0;
+    virtual int profile_step(const char** names, double* ms, int cap) = 0;
+    int N = 0;
+    int64_t step_index = 0;
+    double last_step_ms = 0;
+};
+
+// host-side description of the chart + table, precision independent
+struct HostChart {
+    int V = 0, F = 0;
+    std::vector<double> uv, x3d;
+    std::vector<int> faces;
+    int table_kind = T2D_TABLE_NONE;
+    int tableV = 0;
+    std::vector<uint8_t> table_raw;   // dense table in the caller's stored type
+
+    double table_at(int a, int b) const
+    {
+        size_t k = (size_t)a * tableV + b;
+        switch (table_kind) {
+            case T2D_TABLE_DENSE_F64: return reinterpret_cast<const double*>(table_raw.data())[k];
+            case T2D_TABLE_DENSE_F32: return (double)reinterpret_cast<const float*>(table_raw.data())[k];
+            default: return (double)table_raw[k];
+        }
+    }
+};
+
+template <typename R> class Engine : public EngineBase {
+  public:
+    Engine(const t2d_mesh* mesh, const t2d_table* table, const t2d_params* params, int device);
+    ~Engine() override;
+
+    int set_state(int N, const double* uv, const int* heading, const int* vid, const double* r3d, const uint32_t* ids,
+                  bool project) override;
+    int download(double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, int* face) override;
+    int step(int nsteps) override;
+    int step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color) override;
+    int observables(double* out) override;
+    int get_counters(t2d_counters* out) override;
+    int reset_counters() override;
+    int set_params(const t2d_params* p) override;
+    int get_r3d(int N, const double* uv, double* r3d, int* vid, int* face) override;
+    int tiling(int N, double* uv_old, double* uv, int* heading) override;
+    int unit_vectors(int N, const int* heading, double* out) override;
+    int forces(double* F, int* new_heading, int* color) override;
+    int hop_table(uint8_t* out) override;
+    int profile_step(const char** names, double* ms, int cap) override;
+
+  private:
+    void upload_chart();
+    void build_csr();
+    void build_hop_table_device(std::vector<uint8_t>* host_out);
+    void apply_params();
+    void one_step(bool moving, cudaEvent_t* ev, int* nev);
+    int read_fault();
+    void ingest(int N, const double* uv, const int* heading, const int* vid, const double* r3d, const uint32_t* ids,
+                ParticleArrays<R>& dst, bool separate_origin);
+
+    int device_ = 0, sm_count_ = 148;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    t2d_params P_;
+    HostChart chart_;
+    int capacity_ = 0;
+    bool have_ids_ = false;
+    int64_t launches_ = 0, steps_ = 0;
+
+    // chart
+    DevBuf<TriUV<R>> d_tri_;
+    DevBuf<int4> d_tri_vid_;
+    DevBuf<Pos3<R>> d_x3d_;
+    DevBuf<int> d_gstart_, d_gfaces_;
+    DevBuf<double2> d_trig_d_;
+    DevBuf<float2> d_trig_f_;
+    DevBuf<int> d_csr_start_, d_csr_col_;
+    DevBuf<double> d_csr_d_;
+    DevBuf<int> d_adj_start_, d_adj_;
+    // particles
+    DevBuf<Real2<R>> d_uv_[2], d_uv_new_, d_rdot_, d_F_;
+    DevBuf<int2> d_hv_[2];
+    DevBuf<Pos3<R>> d_X_[2];
+    DevBuf<int> d_face_[2], d_new_heading_, d_color_;
+    DevBuf<uint32_t> d_id_[2], d_origin_[2], d_key_, d_rank_;
+    DevBuf<int> d_count_, d_start_, d_blocksums_, d_work_;
+    DevBuf<DevCounters> d_counters_;
+    DevBuf<double> d_obs_;
+    DevBuf<unsigned char> d_stage_in_, d_stage_out_;
+    StepArgs<R> A_;
+};
+
+// ---------------------------------------------------------------------------------------------------
+template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* table, const t2d_params* params, int device)
+{
+    device_ = device;
+    P_ = *params;
+    CK(cudaSetDevice(device_));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_));
+    if (prop.major < 10) throw CudaError{"lib2dtissue_b200 is built for sm_100a (B200) only; device is sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor)};
+    sm_count_ = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0_));
+    CK(cudaEventCreate(&ev1_));
+
+    if (!mesh || mesh->V <= 0 || mesh->F <= 0 || !mesh->uv || !mesh->x3d || !mesh->faces) throw CudaError{"invalid mesh"};
+    chart_.V = mesh->V;
+    chart_.F = mesh->F;
+    chart_.uv.assign(mesh->uv, mesh->uv + 2 * (size_t)mesh->V);
+    chart_.x3d.assign(mesh->x3d, mesh->x3d + 3 * (size_t)mesh->V);
+    chart_.faces.assign(mesh->faces, mesh->faces + 3 * (size_t)mesh->F);
+    for (int v : chart_.faces)
+        if (v < 0 || v >= chart_.V) throw CudaError{"face index out of range"};
+
+    if (table && table->kind != T2D_TABLE_NONE) {
+        chart_.table_kind = table->kind;
+        chart_.tableV = table->V;
+        if (table->V != mesh->V) throw CudaError{"table size does not match the mesh's vertex count"};
+        size_t nn = (size_t)table->V * table->V;
+        if (table->kind == T2D_TABLE_HOPS_FROM_MESH) {
+            // filled after the chart upload (needs the adjacency on the device)
+        } else {
+            if (!table->data) throw CudaError{"table data is null"};
+            size_t es = table->kind == T2D_TABLE_DENSE_F64 ? 8 : (table->kind == T2D_TABLE_DENSE_F32 ? 4 : 1);
+            const uint8_t* src = static_cast<const uint8_t*>(table->data);
+            chart_.table_raw.assign(src, src + nn * es);
+        }
+    }
+    if (P_.neigh_mode == T2D_NEIGH_TABLE && chart_.table_kind == T2D_TABLE_NONE)
+        throw CudaError{"neigh_mode = table needs a vertex-distance table"};
+
+    capacity_ = P_.capacity > 0 ? P_.capacity : 1;
+    upload_chart();
+    if (chart_.table_kind == T2D_TABLE_HOPS_FROM_MESH) {
+        build_hop_table_device(&chart_.table_raw);
+        chart_.table_kind = T2D_TABLE_DENSE_U8;
+    }
+
+    // particle storage
+    const size_t C = (size_t)capacity_;
+    for (int b = 0; b < 2; ++b) {
+        d_uv_[b].alloc(C);
+        d_hv_[b].alloc(C);
+        d_X_[b].alloc(C);
+        d_face_[b].alloc(C);
+        d_id_[b].alloc(C);
+        d_origin_[b].alloc(C);
+    }
+    d_uv_new_.alloc(C);
+    d_rdot_.alloc(C);
+    d_F_.alloc(C);
+    d_new_heading_.alloc(C);
+    d_color_.alloc(C);
+    d_key_.alloc(C);
+    d_rank_.alloc(C);
+    CK(cudaMemsetAsync(d_rdot_.p, 0, C * sizeof(Real2<R>), stream_));
+    CK(cudaMemsetAsync(d_color_.p, 0, C * sizeof(int), stream_));
+    d_counters_.alloc(1);
+    CK(cudaMemsetAsync(d_counters_.p, 0, sizeof(DevCounters), stream_));
+    d_obs_.alloc(T2D_OBS_LEN);
+    d_work_.alloc(4);
+    d_stage_in_.alloc(C * (16 + 4 + 4 + 24 + 4) + 256);
+    d_stage_out_.alloc(C * (16 + 4 + 4 + 24 + 16 + 4 + 4 + 16 + 4) + 256);
+
+    int M;
+    if (P_.neigh_mode == T2D_NEIGH_TABLE) {
+        M = chart_.V;
+    } else {
+        M = 1024;
+        while ((size_t)M < 2 * C) M <<= 1;
+    }
+    A_.M = M;
+    A_.hash_mask = (uint32_t)(M - 1);
+    d_count_.alloc((size_t)M + 8);
+    d_start_.alloc((size_t)M + 8);
+    d_blocksums_.alloc((size_t)scan_blocks(M) + 8);
+    CK(cudaMemsetAsync(d_count_.p, 0, ((size_t)M + 8) * sizeof(int), stream_));
+
+    A_.cur = {d_uv_[0].p, d_hv_[0].p, d_X_[0].p, d_face_[0].p, d_id_[0].p, d_id_[0].p};
+    A_.alt = {d_uv_[1].p, d_hv_[1].p, d_X_[1].p, d_face_[1].p, d_id_[1].p, d_id_[1].p};
+    A_.key = d_key_.p;
+    A_.rank = d_rank_.p;
+    A_.count = d_count_.p;
+    A_.start = d_start_.p;
+    A_.blocksums = d_blocksums_.p;
+    A_.uv_new = d_uv_new_.p;
+    A_.rdot = d_rdot_.p;
+    A_.F = d_F_.p;
+    A_.new_heading = d_new_heading_.p;
+    A_.color = d_color_.p;
+    A_.counters = d_counters_.p;
+    A_.trig_d = d_trig_d_.p;
+    A_.trig_f = d_trig_f_.p;
+    A_.work_counter = d_work_.p;
+    A_.mode = P_.neigh_mode;
+    A_.write_F = 0;
+    apply_params();
+    CK(cudaStreamSynchronize(stream_));
+}
+
+template <typename R> Engine<R>::~Engine()
+{
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+// chart -> device: packed UV triangles, 3-D vertices, uniform UV grid (cell -> faces whose grown bounding
+// box touches the cell, ascending), cos/sin table from the host's libm, vertex adjacency for the BFS
+template <typename R> void Engine<R>::upload_chart()
+{
+    const int V = chart_.V, F = chart_.F;
+    std::vector<TriUV<R>> tri(F);
+    std::vector<int4> tv(F);
+    for (int f = 0; f < F; ++f) {
+        const int* fv = &chart_.faces[3 * (size_t)f];
+        tri[f].ax = (R)chart_.uv[2 * (size_t)fv[0]];
+        tri[f].ay = (R)chart_.uv[2 * (size_t)fv[0] + 1];
+        tri[f].bx = (R)chart_.uv[2 * (size_t)fv[1]];
+        tri[f].by = (R)chart_.uv[2 * (size_t)fv[1] + 1];
+        tri[f].cx = (R)chart_.uv[2 * (size_t)fv[2]];
+        tri[f].cy = (R)chart_.uv[2 * (size_t)fv[2] + 1];
+        tv[f] = make_int4(fv[0], fv[1], fv[2], 0);
+    }
+    std::vector<Pos3<R>> x3(V);
+    double mn[3] = {1e300, 1e300, 1e300};
+    for (int v = 0; v < V; ++v) {
+        x3[v].x = (R)chart_.x3d[3 * (size_t)v];
+        x3[v].y = (R)chart_.x3d[3 * (size_t)v + 1];
+        x3[v].z = (R)chart_.x3d[3 * (size_t)v + 2];
+        x3[v].w = R(0);
+        for (int k = 0; k < 3; ++k) mn[k] = std::min(mn[k], chart_.x3d[3 * (size_t)v + k]);
+    }
+    for (int k = 0; k < 3; ++k) A_.mesh.eucl_origin[k] = (R)mn[k];   // shifted by one cell in apply_params
+    d_tri_.upload(tri, stream_);
+    d_tri_vid_.upload(tv, stream_);
+    d_x3d_.upload(x3, stream_);
+
+    int G = (int)ceil(sqrt((double)F) * 2.0);
+    G = std::max(8, std::min(G, 4096));
+    const double eps = 1e-6;
+    std::vector<int> cnt((size_t)G * G + 1, 0);
+    auto cell_range = [&](int f, int& i0, int& i1, int& j0, int& j1) {
+        const int* fv = &chart_.faces[3 * (size_t)f];
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+        for (int k = 0; k < 3; ++k) {
+            double x = chart_.uv[2 * (size_t)fv[k]], y = chart_.uv[2 * (size_t)fv[k] + 1];
+            x0 = std::min(x0, x);
+            x1 = std::max(x1, x);
+            y0 = std::min(y0, y);
+            y1 = std::max(y1, y);
+        }
+        i0 = std::max(0, (int)floor((x0 - eps) * G));
+        i1 = std::min(G - 1, (int)floor((x1 + eps) * G));
+        j0 = std::max(0, (int)floor((y0 - eps) * G));
+        j1 = std::min(G - 1, (int)floor((y1 + eps) * G));
+    };
+    for (int f = 0; f < F; ++f) {
+        int i0, i1, j0, j1;
+        cell_range(f, i0, i1, j0, j1);
+        for (int j = j0; j <= j1; ++j)
+            for (int i = i0; i <= i1; ++i) cnt[(size_t)j * G + i + 1]++;
+    }
+    std::vector<int> gstart((size_t)G * G + 1, 0);
+    for (size_t c = 0; c < (size_t)G * G; ++c) gstart[c + 1] = gstart[c] + cnt[c + 1];
+    std::vector<int> gfaces((size_t)std::max(1, gstart[(size_t)G * G]));
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int f = 0; f < F; ++f) {   // ascending f => every cell list is ascending
+        int i0, i1, j0, j1;
+        cell_range(f, i0, i1, j0, j1);
+        for (int j = j0; j <= j1; ++j)
+            for (int i = i0; i <= i1; ++i) {
+                size_t c = (size_t)j * G + i;
+                gfaces[(size_t)gstart[c] + cnt[c]++] = f;
+            }
+    }
+    d_gstart_.upload(gstart, stream_);
+    d_gfaces_.upload(gfaces, stream_);
+    A_.mesh.V = V;
+    A_.mesh.F = F;
+    A_.mesh.G = G;
+    A_.mesh.tri = d_tri_.p;
+    A_.mesh.tri_vid = d_tri_vid_.p;
+    A_.mesh.x3d = d_x3d_.p;
+    A_.mesh.gstart = d_gstart_.p;
+    A_.mesh.gfaces = d_gfaces_.p;
+
+    // cos/sin of integer degrees exactly as the reference's libm call sees them:
+    // cos(double(n) * DEG_TO_RAD), LinearAlgebra.cpp:37-41, OrientationHelper.cpp:96-100
+    std::vector<double2> td(TRIG_N);
+    std::vector<float2> tf(TRIG_N);
+    for (int q = 0; q < TRIG_N; ++q) {
+        double angle_degrees = (double)(TRIG_MIN + q);
+        double angle_radians = angle_degrees * DEG_TO_RAD_D;
+        td[q] = make_double2(cos(angle_radians), sin(angle_radians));
+        tf[q] = make_float2((float)td[q].x, (float)td[q].y);
+    }
+    d_trig_d_.upload(td, stream_);
+    d_trig_f_.upload(tf, stream_);
+
+    // vertex adjacency (both directions of every face edge; duplicates are harmless for BFS)
+    std::vector<int> deg((size_t)V + 1, 0);
+    for (int f = 0; f < F; ++f)
+        for (int k = 0; k < 3; ++k) deg[(size_t)chart_.faces[3 * (size_t)f + k] + 1] += 2;
+    std::vector<int> as((size_t)V + 1, 0);
+    for (int v = 0; v < V; ++v) as[v + 1] = as[v] + deg[v + 1];
+    std::vector<int> adj((size_t)std::max(1, as[V])), fill((size_t)V, 0);
+    for (int f = 0; f < F; ++f)
+        for (int k = 0; k < 3; ++k) {
+            int a = chart_.faces[3 * (size_t)f + k], b = chart_.faces[3 * (size_t)f + (k + 1) % 3];
+            adj[(size_t)as[a] + fill[a]++] = b;
+            adj[(size_t)as[b] + fill[b]++] = a;
+        }
+    d_adj_start_.upload(as, stream_);
+    d_adj_.upload(adj, stream_);
+    CK(cudaStreamSynchronize(stream_));
+}
+
+template <typename R> void Engine<R>::build_hop_table_device(std::vector<uint8_t>* host_out)
+{
+    const int V = chart_.V;
+    DevBuf<uint8_t> d_tab;
+    d_tab.alloc((size_t)V * V);
+    int e = launch_hop_table(V, d_adj_start_.p, d_adj_.p, d_tab.p, sm_count_, stream_);
+    if (e != 0) throw CudaError{std::string("hop-table kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
+    launches_++;
+    host_out->resize((size_t)V * V);
+    CK(cudaMemcpyAsync(host_out->data(), d_tab.p, (size_t)V * V, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    chart_.tableV = V;
+}
+
+// thresholded CSR of the table: entries with d < 2σ or d <= color_factor·σ, d = min(D[v][u], D[u][v])
+// (Locomotion.cpp:110 symmetrises by min), kept as doubles — the reference's in-memory precision.
+template <typename R> void Engine<R>::build_csr()
+{
+    const int V = chart_.tableV;
+    const double two_sigma = 2 * P_.sigma, color_r = P_.color_factor * P_.sigma;
+    std::vector<int> start((size_t)V + 1, 0), col;
+    std::vector<double> dv;
+    for (int v = 0; v < V; ++v) {
+        if (chart_.table_at(v, v) != 0.0) throw CudaError{"vertex-distance table must have a zero diagonal"};
+        for (int u = 0; u < V; ++u) {
+            double d = chart_.table_at(v, u), dT = chart_.table_at(u, v);
+            if (dT < d) d = dT;
+            if (d < two_sigma || (d != 0.0 && d <= color_r)) {
+                col.push_back(u);
+                dv.push_back(d);
+            }
+        }
+        start[v + 1] = (int)col.size();
+    }
+    if (col.empty()) {
+        col.push_back(0);
+        dv.push_back(0.0);
+    }
+    d_csr_start_.upload(start, stream_);
+    d_csr_col_.upload(col, stream_);
+    d_csr_d_.upload(dv, stream_);
+    CK(cudaStreamSynchronize(stream_));
+    A_.csr.V = V;
+    A_.csr.start = d_csr_start_.p;
+    A_.csr.col = d_csr_col_.p;
+    A_.csr.d = d_csr_d_.p;
+}
+
+template <typename R> void Engine<R>::apply_params()
+{
+    A_.v0 = (R)P_.v0;
+    A_.k = (R)P_.k;
+    const double two_sigma = 2 * P_.sigma;   // "2 * σ" in double, ForceHelper.cpp:55, OrientationHelper.cpp:58
+    const double color_r = P_.color_factor * P_.sigma;   // "2.4 * σ", 2DTissue.cpp:262
+    A_.two_sigma = (R)two_sigma;
+    A_.color_r = (R)color_r;
+    A_.two_sigma_d = two_sigma;
+    A_.color_r_d = color_r;
+    A_.step_size = (R)P_.step_size;
+    A_.eta360 = P_.eta * 360.0;
+    A_.seed = P_.seed;
+    if (P_.neigh_mode == T2D_NEIGH_EUCLID) {
+        const double rmax = std::max(two_sigma, color_r);
+        const double margin = sizeof(R) == 8 ? 1e-9 : 1e-3;
+        const double cs = 2.0 * rmax * (1.0 + margin);
+        if (!(cs > 0)) throw CudaError{"sigma must be positive"};
+        A_.cell_size = (R)cs;
+        A_.inv_cell = (R)(1.0 / cs);
+        double mn[3] = {1e300, 1e300, 1e300};
+        for (int v = 0; v < chart_.V; ++v)
+            for (int k = 0; k < 3; ++k) mn[k] = std::min(mn[k], chart_.x3d[3 * (size_t)v + k]);
+        for (int k = 0; k < 3; ++k) A_.mesh.eucl_origin[k] = (R)(mn[k] - 2.0 * cs);
+    } else {
+        build_csr();
+    }
+}
+
+template <typename R> int Engine<R>::set_params(const t2d_params* p)
+{
+    if (p->neigh_mode != P_.neigh_mode || p->precision != P_.precision) throw CudaError{"neigh_mode/precision are fixed at create"};
+    int cap = P_.capacity;
+    P_ = *p;
+    P_.capacity = cap;
+    apply_params();
+    return 0;
+}
+
+template <typename R>
+void Engine<R>::ingest(int N, const double* uv, const int* heading, const int* vid, const double* r3d, const uint32_t* ids,
+                       ParticleArrays<R>& dst, bool separate_origin)
+{
+    // raw host arrays -> device staging (sizes of the reference's own arrays) -> SoA conversion on the device
+    unsigned char* base = d_stage_in_.p;
+    size_t off = 0;
+    HostViewIn in{};
+    auto put = [&](const void* src, size_t bytes) -> void* {
+        void* d = base + off;
+        CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream_));
+        off += (bytes + 15) & ~(size_t)15;
+        return d;
+    };
+    in.uv = (const double*)put(uv, sizeof(double) * 2 * (size_t)N);
+    in.heading = heading ? (const int*)put(heading, sizeof(int) * (size_t)N) : nullptr;
+    in.vid = vid ? (const int*)put(vid, sizeof(int) * (size_t)N) : nullptr;
+    in.r3d = r3d ? (const double*)put(r3d, sizeof(double) * 3 * (size_t)N) : nullptr;
+    in.ids = ids ? (const uint32_t*)put(ids, sizeof(uint32_t) * (size_t)N) : nullptr;
+    (void)separate_origin;
+    IoLaunch<R>::ingest(N, in, dst, stream_);
+    launches_++;
+}
+
+template <typename R>
+int Engine<R>::set_state(int N, const double* uv, const int* heading, const int* vid, const double* r3d, const uint32_t* ids,
+                         bool project)
+{
+    if (N < 0 || N > capacity_) throw CudaError{"particle count exceeds the context's capacity"};
+    if (!uv || !heading) throw CudaError{"uv and heading are required"};
+    if (vid && P_.neigh_mode == T2D_NEIGH_TABLE)
+        for (int i = 0; i < N; ++i)
+            if (vid[i] < 0 || vid[i] >= chart_.V) throw CudaError{"vid out of range"};
+    CK(cudaSetDevice(device_));
+    this->N = N;
+    A_.N = N;
+    have_ids_ = ids != nullptr;
+    // index buffers: with caller ids the upload position travels separately, otherwise origin aliases id
+    const int cb = (A_.cur.uv == d_uv_[0].p) ? 0 : 1;
+    A_.cur.origin = have_ids_ ? d_origin_[cb].p : A_.cur.id;
+    A_.alt.origin = have_ids_ ? d_origin_[1 - cb].p : A_.alt.id;
+    ingest(N, uv, heading, vid, r3d, ids, A_.cur, have_ids_);
+    if (project) {
+        Launch<R>::project_only(A_, stream_);
+        launches_++;
+    }
+    CK(cudaMemsetAsync(d_rdot_.p, 0, (size_t)std::max(N, 1) * sizeof(Real2<R>), stream_));
+    CK(cudaMemsetAsync(d_color_.p, 0, (size_t)std::max(N, 1) * sizeof(int), stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return 0;
+}
+
+template <typename R> int Engine<R>::download(double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, int* face)
+{
+    CK(cudaSetDevice(device_));
+    const size_t N = (size_t)this->N;
+    unsigned char* base = d_stage_out_.p;
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> void* {
+        void* d = base + off;
+        off += (bytes + 15) & ~(size_t)15;
+        return d;
+    };
+    HostViewOut o{};
+    if (uv) o.uv = (double*)take(16 * N);
+    if (heading) o.heading = (int*)take(4 * N);
+    if (vid) o.vid = (int*)take(4 * N);
+    if (r3d) o.r3d = (double*)take(24 * N);
+    if (rdot) o.rdot = (double*)take(16 * N);
+    if (color) o.color = (int*)take(4 * N);
+    if (face) o.face = (int*)take(4 * N);
+    IoLaunch<R>::egest((int)N, A_.cur, A_.rdot, A_.color, A_.F, A_.new_heading, o, stream_);
+    launches_++;
+    if (uv) CK(cudaMemcpyAsync(uv, o.uv, 16 * N, cudaMemcpyDeviceToHost, stream_));
+    if (heading) CK(cudaMemcpyAsync(heading, o.heading, 4 * N, cudaMemcpyDeviceToHost, stream_));
+    if (vid) CK(cudaMemcpyAsync(vid, o.vid, 4 * N, cudaMemcpyDeviceToHost, stream_));
+    if (r3d) CK(cudaMemcpyAsync(r3d, o.r3d, 24 * N, cudaMemcpyDeviceToHost, stream_));
+    if (rdot) CK(cudaMemcpyAsync(rdot, o.rdot, 16 * N, cudaMemcpyDeviceToHost, stream_));
+    if (color) CK(cudaMemcpyAsync(color, o.color, 4 * N, cudaMemcpyDeviceToHost, stream_));
+    if (face) CK(cudaMemcpyAsync(face, o.face, 4 * N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return 0;
+}
+
+template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int* nev)
+{
+    auto mark = [&]() {
+        if (ev) CK(cudaEventRecord(ev[(*nev)++], stream_));
+    };
+    A_.step = (uint64_t)step_index;
+    mark();
+    Launch<R>::count_keys(A_, stream_);
+    mark();
+    launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
+    mark();
+    Launch<R>::reorder(A_, stream_);
+    std::swap(A_.cur, A_.alt);
+    mark();
+    if (P_.neigh_mode == T2D_NEIGH_TABLE)
+        Launch<R>::neigh_table(A_, stream_, sm_count_);
+    else
+        Launch<R>::neigh_euclid(A_, stream_);
+    mark();
+    launches_ += 6;
+    if (moving) {
+        Launch<R>::wrap_project(A_, stream_);
+        launches_++;
+        mark();
+        step_index++;
+        steps_++;
+    }
+}
+
+template <typename R> int Engine<R>::read_fault()
+{
+    DevCounters h;
+    CK(cudaMemcpyAsync(&h, d_counters_.p, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    int fault = (int)h.fault;
+    if (fault) {
+        unsigned zero = 0;
+        CK(cudaMemcpyAsync(&d_counters_.p->fault, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream_));
+        CK(cudaStreamSynchronize(stream_));
+    }
+    return fault;
+}
+
+template <typename R> int Engine<R>::step(int nsteps)
+{
+    CK(cudaSetDevice(device_));
+    if (this->N == 0 || nsteps <= 0) return 0;
+    CK(cudaEventRecord(ev0_, stream_));
+    for (int s = 0; s < nsteps; ++s) one_step(true, nullptr, nullptr);
+    CK(cudaEventRecord(ev1_, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    last_step_ms = ms;
+    CK(cudaGetLastError());
+    return read_fault();
+}
+
+template <typename R> int Engine<R>::step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color)
+{
+    set_state(N, uv, heading, vid, r3d, nullptr, false);
+    int fault = step(1);
+    download(uv, heading, vid, r3d, rdot, color, nullptr);
+    return fault;
+}
+
+template <typename R> int Engine<R>::forces(double* F, int* new_heading, int* color)
+{
+    CK(cudaSetDevice(device_));
+    if (this->N == 0) return 0;
+    A_.write_F = 1;
+    one_step(false, nullptr, nullptr);
+    A_.write_F = 0;
+    const size_t N = (size_t)this->N;
+    unsigned char* base = d_stage_out_.p;
+    HostViewOut o{};
+    size_t off = 0;
+    o.F = (double*)(base + off);
+    off += 16 * N;
+    o.new_heading = (int*)(base + off);
+    off += (4 * N + 15) & ~(size_t)15;
+    o.color = (int*)(base + off);
+    IoLaunch<R>::egest((int)N, A_.cur, A_.rdot, A_.color, A_.F, A_.new_heading, o, stream_);
+    launches_++;
+    if (F) CK(cudaMemcpyAsync(F, o.F, 16 * N, cudaMemcpyDeviceToHost, stream_));
+    if (new_heading) CK(cudaMemcpyAsync(new_heading, o.new_heading, 4 * N, cudaMemcpyDeviceToHost, stream_));
+    if (color) CK(cudaMemcpyAsync(color, o.color, 4 * N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R> int Engine<R>::observables(double* out)
+{
+    CK(cudaSetDevice(device_));
+    launch_observables(A_.cur.hv, A_.rdot, sizeof(R) == 4, this->N, d_trig_d_.p, d_obs_.p, stream_);
+    launches_++;
+    double h[T2D_OBS_LEN];
+    CK(cudaMemcpyAsync(h, d_obs_.p, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+    DevCounters c;
+    CK(cudaMemcpyAsync(&c, d_counters_.p, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    const double n = (double)this->N;
+    h[T2D_OBS_COUNT] = n;
+    h[T2D_OBS_PHI] = n > 0 ? sqrt(h[T2D_OBS_SUM_COS] * h[T2D_OBS_SUM_COS] + h[T2D_OBS_SUM_SIN] * h[T2D_OBS_SUM_SIN]) / n : 0;
+    h[T2D_OBS_MEAN_SPEED] = n > 0 ? h[T2D_OBS_SUM_SPEED] / n : 0;
+    h[T2D_OBS_LOST] = (double)c.lost;
+    h[T2D_OBS_NONFINITE] = (double)c.nonfinite;
+    memcpy(out, h, sizeof(h));
+    return 0;
+}
+
+template <typename R> int Engine<R>::get_counters(t2d_counters* out)
+{
+    CK(cudaSetDevice(device_));
+    DevCounters c;
+    CK(cudaMemcpyAsync(&c, d_counters_.p, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    memset(out, 0, sizeof(*out));
+    out->steps = steps_;
+    out->kernel_launches = launches_;
+    out->pairs_in_range = (int64_t)c.pairs_in_range;
+    out->ties_cutoff = (int64_t)c.ties_cutoff;
+    out->ties_trunc = (int64_t)c.ties_trunc;
+    out->wraps = (int64_t)c.wraps;
+    out->wrap_cap_hits = (int64_t)c.wrap_cap_hits;
+    out->order_fallbacks = (int64_t)c.order_fallbacks;
+    out->trig_fallbacks = (int64_t)c.trig_fallbacks;
+    out->locate_fallbacks = (int64_t)c.locate_fallbacks;
+    out->max_row = (int64_t)c.max_row;
+    return 0;
+}
+
+template <typename R> int Engine<R>::reset_counters()
+{
+    CK(cudaSetDevice(device_));
+    CK(cudaMemsetAsync(d_counters_.p, 0, sizeof(DevCounters), stream_));
+    CK(cudaStreamSynchronize(stream_));
+    steps_ = 0;
+    launches_ = 0;
+    return 0;
+}
+
+// CellHelper::get_r3d on caller points, using the spare half of the double buffer as scratch
+template <typename R> int Engine<R>::get_r3d(int N, const double* uv, double* r3d, int* vid, int* face)
+{
+    if (N < 0 || N > capacity_) throw CudaError{"N exceeds the context's capacity"};
+    CK(cudaSetDevice(device_));
+    StepArgs<R> T = A_;
+    T.N = N;
+    T.cur = A_.alt;
+    T.cur.origin = T.cur.id;
+    ingest(N, uv, nullptr, nullptr, nullptr, nullptr, T.cur, false);
+    Launch<R>::project_only(T, stream_);
+    launches_++;
+    HostViewOut o{};
+    unsigned char* base = d_stage_out_.p;
+    o.r3d = (double*)base;
+    o.vid = (int*)(base + 24 * (size_t)N);
+    o.face = (int*)(base + 24 * (size_t)N + ((4 * (size_t)N + 15) & ~(size_t)15));
+    IoLaunch<R>::egest(N, T.cur, A_.rdot, A_.color, A_.F, A_.new_heading, o, stream_);
+    launches_++;
+    if (r3d) CK(cudaMemcpyAsync(r3d, o.r3d, 24 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
+    if (vid) CK(cudaMemcpyAsync(vid, o.vid, 4 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
+    if (face) CK(cudaMemcpyAsync(face, o.face, 4 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R> int Engine<R>::tiling(int N, double* uv_old, double* uv, int* heading)
+{
+    if (N < 0 || N > capacity_) throw CudaError{"N exceeds the context's capacity"};
+    CK(cudaSetDevice(device_));
+    unsigned char* base = d_stage_in_.p;
+    double* s_old = (double*)base;
+    double* s_new = (double*)(base + 16 * (size_t)N);
+    CK(cudaMemcpyAsync(s_old, uv_old, 16 * (size_t)N, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(s_new, uv, 16 * (size_t)N, cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(A_.new_heading, heading, 4 * (size_t)N, cudaMemcpyHostToDevice, stream_));
+    Real2<R>* d_old = A_.alt.uv;
+    Real2<R>* d_new = A_.uv_new;
+    IoLaunch<R>::in2(N, s_old, d_old, stream_);
+    IoLaunch<R>::in2(N, s_new, d_new, stream_);
+    Launch<R>::tiling_only(A_, d_old, d_new, A_.new_heading, N, stream_);
+    double* o_old = (double*)d_stage_out_.p;
+    double* o_new = (double*)(d_stage_out_.p + 16 * (size_t)N);
+    IoLaunch<R>::out2(N, d_old, o_old, stream_);
+    IoLaunch<R>::out2(N, d_new, o_new, stream_);
+    launches_ += 5;
+    CK(cudaMemcpyAsync(uv_old, o_old, 16 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(uv, o_new, 16 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(heading, A_.new_heading, 4 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    return read_fault();
+}
+
+template <typename R> int Engine<R>::unit_vectors(int N, const int* heading, double* out)
+{
+    if (N < 0 || N > capacity_) throw CudaError{"N exceeds the context's capacity"};
+    CK(cudaSetDevice(device_));
+    CK(cudaMemcpyAsync(A_.new_heading, heading, 4 * (size_t)N, cudaMemcpyHostToDevice, stream_));
+    R* tmp = reinterpret_cast<R*>(A_.uv_new);
+    Launch<R>::unit_vectors(A_, A_.new_heading, tmp, N, stream_);
+    double* o = (double*)d_stage_out_.p;
+    IoLaunch<R>::outN(N, 2, tmp, o, stream_);
+    launches_ += 2;
+    CK(cudaMemcpyAsync(out, o, 16 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R> int Engine<R>::hop_table(uint8_t* out)
+{
+    CK(cudaSetDevice(device_));
+    std::vector<uint8_t> h;
+    build_hop_table_device(&h);
+    memcpy(out, h.data(), h.size());
+    return 0;
+}
+
+template <typename R> int Engine<R>::profile_step(const char** names, double* ms, int cap)
+{
+    CK(cudaSetDevice(device_));
+    if (this->N == 0) return 0;
+    static const char* kNames[] = {"count_keys", "scan", "reorder", "neigh_force_align", "wrap_project"};
+    cudaEvent_t ev[8];
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    int nev = 0;
+    one_step(true, ev, &nev);
+    CK(cudaStreamSynchronize(stream_));
+    int n = std::min(cap, nev - 1);
+    for (int i = 0; i < n; ++i) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        names[i] = kNames[i];
+        ms[i] = t;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    read_fault();
+    return n;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------------
+struct t2d_ctx {
+    std::string err;
+    std::unique_ptr<EngineBase> eng;
+};
+
+#define T2D_TRY(ctx, body)                          \
+    try {                                           \
+        body                                        \
+    } catch (const CudaError& e) {                  \
+        (ctx)->err = e.msg;                         \
+        return -1;                                  \
+    } catch (const std::exception& e) {             \
+        (ctx)->err = e.what();                      \
+        return -1;                                  \
+    }
+
+extern "C" {
+
+int t2d_version(void) { return 100; }
+
+int t2d_create(const t2d_mesh* mesh, const t2d_table* table, const t2d_params* params, int device, t2d_ctx** out)
+{
+    if (!out || !params) {
+        g_create_error = "null argument";
+        return -1;
+    }
+    *out = nullptr;
+    std::unique_ptr<t2d_ctx> c(new t2d_ctx());
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                             " — lib2dtissue_b200 has no CPU fallback";
+            return -1;
+        }
+        if (params->precision == T2D_PRECISION_FP32)
+            c->eng.reset(new Engine<float>(mesh, table, params, device));
+        else
+            c->eng.reset(new Engine<double>(mesh, table, params, device));
+    } catch (const CudaError& e) {
+        g_create_error = e.msg;
+        return -1;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return -1;
+    }
+    *out = c.release();
+    return 0;
+}
+
+void t2d_destroy(t2d_ctx* ctx) { delete ctx; }
+
+const char* t2d_last_error(const t2d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int t2d_set_particles(t2d_ctx* ctx, int32_t N, const double* uv, const int32_t* heading, const uint32_t* ids)
+{
+    T2D_TRY(ctx, return ctx->eng->set_state(N, uv, heading, nullptr, nullptr, ids, true);)
+}
+int t2d_set_state(t2d_ctx* ctx, int32_t N, const double* uv, const int32_t* heading, const int32_t* vid, const double* r3d,
+                  const uint32_t* ids)
+{
+    T2D_TRY(ctx, return ctx->eng->set_state(N, uv, heading, vid, r3d, ids, false);)
+}
+int t2d_download(t2d_ctx* ctx, double* uv, int32_t* heading, int32_t* vid, double* r3d, double* rdot, int32_t* color,
+                 int32_t* face)
+{
+    T2D_TRY(ctx, return ctx->eng->download(uv, heading, vid, r3d, rdot, color, face);)
+}
+int32_t t2d_particle_count(const t2d_ctx* ctx) { return ctx->eng->N; }
+int t2d_step(t2d_ctx* ctx, int32_t nsteps) { T2D_TRY(ctx, return ctx->eng->step(nsteps);) }
+int t2d_step_host(t2d_ctx* ctx, int32_t N, double* uv, int32_t* heading, int32_t* vid, double* r3d, double* rdot,
+                  int32_t* color)
+{
+    T2D_TRY(ctx, return ctx->eng->step_host(N, uv, heading, vid, r3d, rdot, color);)
+}
+int t2d_observables(t2d_ctx* ctx, double out[T2D_OBS_LEN]) { T2D_TRY(ctx, return ctx->eng->observables(out);) }
+int t2d_get_counters(t2d_ctx* ctx, t2d_counters* out) { T2D_TRY(ctx, return ctx->eng->get_counters(out);) }
+int t2d_reset_counters(t2d_ctx* ctx) { T2D_TRY(ctx, return ctx->eng->reset_counters();) }
+int64_t t2d_get_step(const t2d_ctx* ctx) { return ctx->eng->step_index; }
+int t2d_set_step(t2d_ctx* ctx, int64_t step)
+{
+    ctx->eng->step_index = step;
+    return 0;
+}
+int t2d_set_params(t2d_ctx* ctx, const t2d_params* params) { T2D_TRY(ctx, return ctx->eng->set_params(params);) }
+int t2d_get_r3d(t2d_ctx* ctx, int32_t N, const double* uv, double* r3d, int32_t* vid, int32_t* face)
+{
+    T2D_TRY(ctx, return ctx->eng->get_r3d(N, uv, r3d, vid, face);)
+}
+int t2d_tiling(t2d_ctx* ctx, int32_t N, double* uv_old, double* uv, int32_t* heading)
+{
+    T2D_TRY(ctx, return ctx->eng->tiling(N, uv_old, uv, heading);)
+}
+int t2d_angles_to_unit_vectors(t2d_ctx* ctx, int32_t N, const int32_t* heading, double* out)
+{
+    T2D_TRY(ctx, return ctx->eng->unit_vectors(N, heading, out);)
+}
+int t2d_forces(t2d_ctx* ctx, double* F, int32_t* new_heading, int32_t* color)
+{
+    T2D_TRY(ctx, return ctx->eng->forces(F, new_heading, color);)
+}
+int t2d_build_hop_table(t2d_ctx* ctx, uint8_t* out) { T2D_TRY(ctx, return ctx->eng->hop_table(out);) }
+double t2d_last_step_ms(const t2d_ctx* ctx) { return ctx->eng->last_step_ms; }
+int t2d_profile_step(t2d_ctx* ctx, const char** names, double* ms, int cap)
+{
+    T2D_TRY(ctx, return ctx->eng->profile_step(names, ms, cap);)
+}
+
+void* t2d_pinned_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void t2d_pinned_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// multi-GPU entry points live in comm.cu
+
+}  // extern "C"

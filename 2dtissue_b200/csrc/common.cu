@@ -1,0 +1,191 @@
+// common.cu — precision-independent kernels: exclusive scan of the bucket histogram, observables.
+#include "t2d_internal.h"
+
+namespace t2d {
+
+// ---------------------------------------------------------------------------------------------------
+// exclusive scan of count[0..M) into start[0..M], zeroing count for the next step.
+// Three launches: per-tile sums -> scan of the tile sums (one block) -> per-tile scan + offset.
+// A tile is 1024 threads x 4 ints (16-byte loads).  M is padded to a multiple of 4 by the allocator.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_TILE = SCAN_THREADS * 4;
+
+int scan_blocks(int M) { return (M + SCAN_TILE - 1) / SCAN_TILE; }
+
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// inclusive scan across the block; returns this thread's inclusive value and the block total
+__device__ __forceinline__ int block_incl_scan(int v, int* total)
+{
+    __shared__ int s_w[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = warp_incl_scan(v);
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int t = (lane < (int)(blockDim.x >> 5)) ? s_w[lane] : 0;
+        t = warp_incl_scan(t);
+        s_w[lane] = t;
+    }
+    __syncthreads();
+    int base = (w > 0) ? s_w[w - 1] : 0;
+    *total = s_w[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return inc + base;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const int* __restrict__ count, int* __restrict__ sums, int M)
+{
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    int v = 0;
+    if (base + 3 < M) {
+        int4 q = *reinterpret_cast<const int4*>(count + base);
+        v = q.x + q.y + q.z + q.w;
+    } else {
+        for (int k = 0; k < 4; ++k)
+            if (base + k < M) v += count[base + k];
+    }
+    int total;
+    block_incl_scan(v, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(int* sums, int nb)
+{
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
+        int i = b0 + threadIdx.x;
+        int v = (i < nb) ? sums[i] : 0;
+        int total;
+        int inc = block_incl_scan(v, &total);
+        int c = carry;
+        if (i < nb) sums[i] = c + inc - v;   // exclusive
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[nb] = carry;   // grand total
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int* __restrict__ count, int* __restrict__ start,
+                                                             const int* __restrict__ sums, int M, int nb)
+{
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    int q[4] = {0, 0, 0, 0};
+    if (base + 3 < M) {
+        int4 t = *reinterpret_cast<const int4*>(count + base);
+        q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
+        *reinterpret_cast<int4*>(count + base) = make_int4(0, 0, 0, 0);
+    } else {
+        for (int k = 0; k < 4; ++k)
+            if (base + k < M) {
+                q[k] = count[base + k];
+                count[base + k] = 0;
+            }
+    }
+    int v = q[0] + q[1] + q[2] + q[3];
+    int total;
+    int inc = block_incl_scan(v, &total);
+    int off = sums[blockIdx.x] + inc - v;
+    if (base + 3 < M) {
+        int4 o;
+        o.x = off;
+        o.y = off + q[0];
+        o.z = o.y + q[1];
+        o.w = o.z + q[2];
+        *reinterpret_cast<int4*>(start + base) = o;
+    } else {
+        int r = off;
+        for (int k = 0; k < 4; ++k)
+            if (base + k < M) {
+                start[base + k] = r;
+                r += q[k];
+            }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) start[M] = sums[nb];
+}
+
+void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s)
+{
+    const int nb = scan_blocks(M);
+    k_scan_tile_sums<<<nb, SCAN_THREADS, 0, s>>>(count, blocksums, M);
+    k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(blocksums, nb);
+    k_scan_apply<<<nb, SCAN_THREADS, 0, s>>>(count, start, blocksums, M, nb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// observables: sum cos n, sum sin n, sum |rdot| over the resident particles
+// ---------------------------------------------------------------------------------------------------
+template <typename R2>
+__global__ void __launch_bounds__(256) k_observables(const int2* __restrict__ hv, const R2* __restrict__ rdot, int N,
+                                                     const double2* __restrict__ trig, double* out)
+{
+    double sc = 0, ss = 0, sp = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        int n = hv[i].x;
+        double c, s;
+        if (n >= TRIG_MIN && n <= TRIG_MAX) {
+            double2 t = trig[n - TRIG_MIN];
+            c = t.x;
+            s = t.y;
+        } else {
+            double r = (double)n * DEG_TO_RAD_D;
+            c = cos(r);
+            s = sin(r);
+        }
+        sc += c;
+        ss += s;
+        double rx = (double)rdot[i].x, ry = (double)rdot[i].y;
+        sp += sqrt(rx * rx + ry * ry);
+    }
+    __shared__ double sh[3][8];
+    for (int o = 16; o > 0; o >>= 1) {
+        sc += __shfl_down_sync(0xffffffffu, sc, o);
+        ss += __shfl_down_sync(0xffffffffu, ss, o);
+        sp += __shfl_down_sync(0xffffffffu, sp, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh[0][w] = sc;
+        sh[1][w] = ss;
+        sh[2][w] = sp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int k = 0; k < 8; ++k) {
+            a += sh[0][k];
+            b += sh[1][k];
+            c += sh[2][k];
+        }
+        atomicAdd(&out[T2D_OBS_SUM_COS], a);
+        atomicAdd(&out[T2D_OBS_SUM_SIN], b);
+        atomicAdd(&out[T2D_OBS_SUM_SPEED], c);
+    }
+}
+
+void launch_observables(const int2* hv, const void* rdot, int is_f32, int N, const double2* trig, double* out8, cudaStream_t s)
+{
+    cudaMemsetAsync(out8, 0, sizeof(double) * T2D_OBS_LEN, s);
+    if (N <= 0) return;
+    int grid = (N + 255) / 256;
+    if (grid > 1184) grid = 1184;   // 148 SMs x 8 resident blocks
+    if (is_f32)
+        k_observables<Real2<float>><<<grid, 256, 0, s>>>(hv, (const Real2<float>*)rdot, N, trig, out8);
+    else
+        k_observables<Real2<double>><<<grid, 256, 0, s>>>(hv, (const Real2<double>*)rdot, N, trig, out8);
+}
+
+}  // namespace t2d

@@ -1,0 +1,143 @@
+// io_kernels.cuh — conversion between the reference's host layouts (Eigen column-major doubles, int32) and
+// the device SoA state.  Raw host arrays are copied to a device staging area and converted there, so the
+// PCIe traffic of t2d_step_host is exactly the reference's own array sizes.
+#pragma once
+#include "t2d_internal.h"
+
+namespace t2d {
+
+struct HostViewIn {        // device copies of the caller's arrays (any may be null)
+    const double* uv;      // [2N]
+    const int* heading;    // [N]
+    const int* vid;        // [N]
+    const double* r3d;     // [3N]
+    const uint32_t* ids;   // [N]
+};
+struct HostViewOut {
+    double* uv;
+    int* heading;
+    int* vid;
+    double* r3d;
+    double* rdot;
+    int* color;
+    int* face;
+    double* F;
+    int* new_heading;
+};
+
+template <typename R> __global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleArrays<R> p)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Real2<R> u = {(R)in.uv[i], (R)in.uv[N + i]};
+    p.uv[i] = u;
+    int2 hv = {in.heading ? in.heading[i] : 0, in.vid ? in.vid[i] : 0};
+    p.hv[i] = hv;
+    Pos3<R> X = {R(0), R(0), R(0), R(0)};
+    if (in.r3d) {
+        X.x = (R)in.r3d[i];
+        X.y = (R)in.r3d[N + i];
+        X.z = (R)in.r3d[2 * N + i];
+    }
+    p.X[i] = X;
+    p.face[i] = -1;
+    p.id[i] = in.ids ? in.ids[i] : (uint32_t)i;
+    if (p.origin != p.id) p.origin[i] = (uint32_t)i;
+}
+
+// slot s holds the particle that sits at index origin[s] of the caller's arrays
+template <typename R>
+__global__ void __launch_bounds__(256) k_egest(int N, ParticleArrays<R> p, const Real2<R>* rdot, const int* color,
+                                               const Real2<R>* F, const int* new_heading, HostViewOut out)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const int o = (int)p.origin[s];
+    if (out.uv) {
+        Real2<R> u = p.uv[s];
+        out.uv[o] = (double)u.x;
+        out.uv[N + o] = (double)u.y;
+    }
+    if (out.heading || out.vid) {
+        int2 hv = p.hv[s];
+        if (out.heading) out.heading[o] = hv.x;
+        if (out.vid) out.vid[o] = hv.y;
+    }
+    if (out.r3d) {
+        Pos3<R> X = p.X[s];
+        out.r3d[o] = (double)X.x;
+        out.r3d[N + o] = (double)X.y;
+        out.r3d[2 * N + o] = (double)X.z;
+    }
+    if (out.rdot) {
+        Real2<R> r = rdot[s];
+        out.rdot[o] = (double)r.x;
+        out.rdot[N + o] = (double)r.y;
+    }
+    if (out.color) out.color[o] = color[s];
+    if (out.face) out.face[o] = p.face[s];
+    if (out.F) {
+        Real2<R> f = F[s];
+        out.F[o] = (double)f.x;
+        out.F[N + o] = (double)f.y;
+    }
+    if (out.new_heading) out.new_heading[o] = new_heading[s];
+}
+
+template <typename R> __global__ void __launch_bounds__(256) k_in2(int N, const double* src, Real2<R>* dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Real2<R> u = {(R)src[i], (R)src[N + i]};
+    dst[i] = u;
+}
+template <typename R> __global__ void __launch_bounds__(256) k_out2(int N, const Real2<R>* src, double* dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Real2<R> u = src[i];
+    dst[i] = (double)u.x;
+    dst[N + i] = (double)u.y;
+}
+template <typename R> __global__ void __launch_bounds__(256) k_outN(int N, int cols, const R* src, double* dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * cols) return;
+    dst[i] = (double)src[i];
+}
+
+template <typename R> struct IoLaunch {
+    static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s);
+    static void egest(int N, const ParticleArrays<R>& p, const Real2<R>* rdot, const int* color, const Real2<R>* F,
+                      const int* new_heading, const HostViewOut& out, cudaStream_t s);
+    static void in2(int N, const double* src, Real2<R>* dst, cudaStream_t s);
+    static void out2(int N, const Real2<R>* src, double* dst, cudaStream_t s);
+    static void outN(int N, int cols, const R* src, double* dst, cudaStream_t s);
+};
+
+#ifdef T2D_IO_IMPL
+template <typename R> void IoLaunch<R>::ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s)
+{
+    if (N > 0) k_ingest<R><<<(N + 255) / 256, 256, 0, s>>>(N, in, p);
+}
+template <typename R>
+void IoLaunch<R>::egest(int N, const ParticleArrays<R>& p, const Real2<R>* rdot, const int* color, const Real2<R>* F,
+                        const int* new_heading, const HostViewOut& out, cudaStream_t s)
+{
+    if (N > 0) k_egest<R><<<(N + 255) / 256, 256, 0, s>>>(N, p, rdot, color, F, new_heading, out);
+}
+template <typename R> void IoLaunch<R>::in2(int N, const double* src, Real2<R>* dst, cudaStream_t s)
+{
+    if (N > 0) k_in2<R><<<(N + 255) / 256, 256, 0, s>>>(N, src, dst);
+}
+template <typename R> void IoLaunch<R>::out2(int N, const Real2<R>* src, double* dst, cudaStream_t s)
+{
+    if (N > 0) k_out2<R><<<(N + 255) / 256, 256, 0, s>>>(N, src, dst);
+}
+template <typename R> void IoLaunch<R>::outN(int N, int cols, const R* src, double* dst, cudaStream_t s)
+{
+    if (N > 0) k_outN<R><<<(N * cols + 255) / 256, 256, 0, s>>>(N, cols, src, dst);
+}
+#endif
+
+}  // namespace t2d
