@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of 2DTissue's per-timestep particle update on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU step (rank 0 only)
+
+A "step" is one pass of the hot path (bin -> sort -> neighbour/force/align -> Euler -> seam re-entry ->
+re-projection) over all resident particles.  Workload (config.workload):
+    c4shard  (default) the per-GPU shard of BASELINE.json configs[3]: 2M particles per GPU (16M on 8 GPUs), refined
+             ("high-resolution") ellipsoid chart, Euclidean neighbour cutoff, fp32 fast path, weak scaling
+    c2       configs[1]: 10k particles, Euclidean cutoff        c3  configs[2]: 1M particles, table criterion
+One JSON line is printed by rank 0.  `value` = whole-job particle-steps/s with the state resident in HBM;
+`e2e` = the same metric through t2d_step_host() with pinned HOST buffers (H2D + step + D2H every step).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SURFACE_AREA = 451.3          # ellipsoid_x4 surface area in mesh units^2
+# algorithmic bytes per particle-step, SURVEY.md §8(d)
+B_ALG = {("f32", "table"): 144, ("f32", "euclid"): 192, ("f64", "table"): 208, ("f64", "euclid"): 280}
+# per-kernel algorithmic bytes per particle (same table, split by stage)
+B_KERNEL = {
+    "f32": {"count_keys": 16 + 8, "scan": 0, "reorder": 36 + 16 + 8, "neigh_force_align": 24 + 16, "wrap_project": 68},
+    "f64": {"count_keys": 32 + 8, "scan": 0, "reorder": 52 + 32 + 8, "neigh_force_align": 36 + 24, "wrap_project": 104},
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload_spec(args, world):
+    w = args.workload
+    if w == "c4shard":
+        per = args.particles_per_gpu or 2_000_000
+        return dict(name="c4shard: %d particles/GPU, refined ellipsoid chart (2 levels), Euclidean cutoff" % per,
+                    per_gpu=per, total=per * world, mode="euclid", refine=2, dtype=args.dtype or "f32")
+    if w == "c2":
+        return dict(name="c2: 10k particles, ellipsoid_x4 chart, Euclidean cutoff", per_gpu=10_000, total=10_000 * world,
+                    mode="euclid", refine=0, dtype=args.dtype or "f32")
+    if w == "c3":
+        return dict(name="c3: 1M particles, ellipsoid_x4 chart, hop-count vertex-distance table", per_gpu=1_000_000,
+                    total=1_000_000 * world, mode="table", refine=0, dtype=args.dtype or "f32")
+    raise SystemExit("unknown workload " + w)
+
+
+def sigma_for(total):
+    return float(np.sqrt(0.5 * SURFACE_AREA / (np.pi * total)))   # packing fraction 0.5
+
+
+def load_chart(t2d, refine):
+    chart = t2d.load_chart(os.path.join(ROOT, "tests", "golden", "ellipsoid_x4.t2dchart"))
+    if refine:
+        chart = t2d.refine_chart(chart, refine)
+    return chart
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path, bounded sample
+# ------------------------------------------------------------------------------------------------------
+def run_reference_sample(spec, steps, warmup, seconds_budget=25.0):
+    """Returns (particle_steps_per_s, cores, kind, sample_text)."""
+    t2d = importlib.import_module("2dtissue_b200")
+    chart = load_chart(t2d, 0)   # the compiled reference walks ALL faces per particle: keep its own mesh
+    from oracle import refbind, oraclebind
+    mode = 1 if spec["mode"] == "euclid" else 0
+    if refbind.available():
+        ref = refbind.Ref()
+        ref.chart_import(chart)
+        if mode == 0:
+            ref.table_import(oraclebind.Oracle(chart).build_hop_table())
+        Ns = 1500
+        sigma = sigma_for(Ns) if mode == 1 else 0.4166666666666667
+        uv, n = t2d.seed_particles(Ns, seed=1234)
+        r3d, vid = ref.get_r3d(uv)
+        st = dict(uv=uv, n=n, vid=vid, r3d=r3d)
+        for _ in range(max(1, min(warmup, 1))):
+            st = ref.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode)
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            st = ref.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode)
+            done += 1
+            if time.perf_counter() - t0 > seconds_budget:
+                break
+        dt = time.perf_counter() - t0
+        return Ns * done / dt, 1, "reference", ("compiled reference (oracle/_ref), single thread (it has none), %d particles x %d "
+                                               "steps on ellipsoid_x4, %s criterion; O(N^2): cannot hold the full workload" %
+                                               (Ns, done, spec["mode"]))
+    orc = oraclebind.Oracle(chart)
+    if mode == 0:
+        orc.set_table(orc.build_hop_table())
+    Ns = 200_000 if mode == 1 else 50_000
+    sigma = sigma_for(Ns) if mode == 1 else 0.4166666666666667
+    uv, n = t2d.seed_particles(Ns, seed=1234)
+    r3d, vid, _ = orc.get_r3d(uv)
+    st = dict(uv=uv, n=n, vid=vid, r3d=r3d)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode, threads=cores)
+        done += 1
+        if time.perf_counter() - t0 > seconds_budget:
+            break
+    dt = time.perf_counter() - t0
+    return Ns * done / dt, cores, "port", "oracle port (OpenMP, %d threads), %d particles x %d steps" % (cores, Ns, done)
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    spec = workload_spec(args, world)
+    v, cores, kind, sample = run_reference_sample(spec, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "particle_steps_per_sec", "value": v, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": spec["name"]},
+            "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def main_ours(args, rank, world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: lib2dtissue_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t2d = importlib.import_module("2dtissue_b200")
+    spec = workload_spec(args, world)
+    chart = load_chart(t2d, spec["refine"])
+    mode = t2d.NEIGH_EUCLID if spec["mode"] == "euclid" else t2d.NEIGH_TABLE
+    prec = t2d.PRECISION_FP32 if spec["dtype"] == "f32" else t2d.PRECISION_FP64
+    Nloc = spec["per_gpu"]
+    sigma = sigma_for(spec["total"]) if mode == t2d.NEIGH_EUCLID else 0.4166666666666667
+    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=Nloc, device=local_rank)
+    if mode == t2d.NEIGH_TABLE:
+        kw["table_kind"] = t2d.TABLE_HOPS_FROM_MESH
+    ctx = t2d.Context(chart, **kw)
+    uv, n = t2d.seed_particles(Nloc, seed=1234 + rank)
+    ctx.set_particles(uv, n, ids=(np.arange(Nloc, dtype=np.uint32) + np.uint32(rank * Nloc)) if world > 1 else None)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        ctx.step(1)
+    barrier()
+    ctx.reset_counters()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    fault = ctx.step(args.steps)            # K steps back to back on the library's stream, synchronised at the end
+    dev_ms = ctx.last_step_ms               # CUDA events on that stream around exactly these K steps
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.counters()["kernel_launches"]
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = spec["total"] * args.steps / (dev_ms * 1e-3)
+
+    # per-kernel CUDA-event breakdown (extra steps, outside the timed region)
+    prof = {}
+    for _ in range(5):
+        for name, ms in ctx.profile_step():
+            prof.setdefault(name, []).append(ms)
+    prof = {k: statistics.median(v) for k, v in prof.items()}
+
+    # end-to-end through the drop-in call with pinned host buffers
+    e2e_steps = max(2, min(args.steps, 10))
+    s = ctx.download(("uv", "n", "vid", "r3d"))
+    pin = lambda a: torch.from_numpy(a.copy()).pin_memory().numpy()
+    h_uv, h_n, h_vid, h_r3d = pin(s["uv"]), pin(s["n"]), pin(s["vid"]), pin(s["r3d"])
+    h_rdot, h_col = pin(np.zeros(2 * Nloc)), pin(np.zeros(Nloc, dtype=np.int32))
+    ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col)
+    barrier()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col)
+    barrier()
+    e2e_s = time.perf_counter() - te
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = spec["total"] * e2e_steps / float(t.item())
+    h2d = Nloc * (16 + 4 + 4 + 24)
+    d2h = Nloc * (16 + 4 + 4 + 24 + 16 + 4)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        key = (spec["dtype"], spec["mode"])
+        dom = max(prof, key=prof.get) if prof else None
+        roof = None
+        if dom:
+            bk = B_KERNEL[spec["dtype"]][dom] + (16 if (spec["mode"] == "euclid" and dom in ("reorder", "neigh_force_align")) else 0)
+            ach = bk * Nloc / (prof[dom] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel_ms": prof[dom], "alg_bytes_per_particle": bk,
+                    "step_alg_bytes_per_particle": B_ALG[key],
+                    "step_achieved_gbs": B_ALG[key] * Nloc / (ms_per_step * 1e-3) / 1e9,
+                    "step_frac": B_ALG[key] * Nloc / (ms_per_step * 1e-3) / 1e9 / peak}
+        cpu_v, cores, kind, sample = run_reference_sample(spec, 3, 1, seconds_budget=20.0)
+        line = {"metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic",
+                "config": {"workload": spec["name"], "particles_total": spec["total"], "sigma": sigma,
+                           "mesh_V": int(len(chart["uv"])), "mesh_F": int(len(chart["faces"])),
+                           "l2": "per-step working set (%d MB) exceeds the 126 MB L2; no explicit flush" %
+                                 int(Nloc * 112 / 1e6 + 32), "parallelism": "slab%d" % world if world > 1 else "single",
+                           "fault": fault},
+                "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
+                "kernel_ms": prof, "roofline": roof,
+                "cpu_baseline": {"value": cpu_v, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d * world),
+                        "d2h_bytes_per_step": int(d2h * world), "steps": e2e_steps}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4shard", choices=["c4shard", "c2", "c3"])
+    ap.add_argument("--particles-per-gpu", type=int, default=0)
+    ap.add_argument("--dtype", default=None, choices=[None, "f32", "f64"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+    else:
+        main_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,7 @@ def lib():
         L.t2do_table_u8.restype = C.POINTER(C.c_ubyte)
         L.t2do_table_u8.argtypes = [C.c_void_p]
         L.t2do_inject_noise.argtypes = [C.c_void_p, _dp]
+        L.t2do_set_angle_out.argtypes = [C.c_void_p, _dp]
         L.t2do_get_r3d.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _ip, _ip, C.c_int, C.POINTER(Stats)]
         L.t2do_tiling.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _ip, C.POINTER(Stats)]
         L.t2do_step.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, _dp, _ip, _ip, _dp, _up, C.c_uint64, _dp, _ip,
@@ -153,12 +154,15 @@ class Oracle:
             self.L.t2do_inject_noise(self.ctx, _d(eta_inject))
         else:
             self.L.t2do_inject_noise(self.ctx, None)
+        angle = np.zeros(N)
+        self.L.t2do_set_angle_out(self.ctx, _d(angle))
         fault = self.L.t2do_step(self.ctx, C.byref(P), N, _d(uv), _i(n), _i(vid), _d(r3d), ids_p, step_index, _d(rdot),
                                  _i(color), _d(F), _i(face), C.byref(st))
+        self.L.t2do_set_angle_out(self.ctx, None)
         if fault < 0:
             raise RuntimeError("oracle step failed: %d" % fault)
         self.last_stats = st.as_dict()
-        return dict(uv=uv, n=n, vid=vid, r3d=r3d, rdot=rdot, color=color, F=F, face=face, fault=fault,
+        return dict(uv=uv, n=n, vid=vid, r3d=r3d, rdot=rdot, color=color, F=F, face=face, fault=fault, angle=angle,
                     stats=st.as_dict())
 
     def observables(self, n, rdot):

@@ -5,7 +5,7 @@
  * formed: the reference is built for baseline x86-64 (no FMA) and the arithmetic must round identically.
  *
  * Parity status: PINNED — against the reference's own test vectors (tests/test_oracle_kat.py) and
- * against outputs of the compiled reference (tests/golden/*.npz, tests/test_oracle_vs_reference.py).
+ * against outputs of the compiled reference (tests/golden/ npz, tests/test_oracle_vs_reference.py).
  */
 #include "t2d_oracle.h"
 
@@ -32,6 +32,7 @@ struct t2do_ctx {
     /* UV grid for point location */
     int G;
     int *gstart, *gfaces;
+    double* angle_out;        /* optional: receives every particle's mean angle in degrees (before truncation) */
     const double* eta_inject; /* optional per-particle noise (degrees) replacing the Philox draw; borrowed */
     /* table-mode CSR cache */
     double csr_rmax;
@@ -568,6 +569,7 @@ int t2do_set_table_u8(t2do_ctx* c, int V, const uint8_t* D)
 const uint8_t* t2do_table_u8(t2do_ctx* c) { return c->Du8; }
 
 void t2do_inject_noise(t2do_ctx* c, const double* eta_deg) { c->eta_inject = eta_deg; }
+void t2do_set_angle_out(t2do_ctx* c, double* buf) { c->angle_out = buf; }
 
 static inline double table_at(const t2do_ctx* c, int a, int b)
 {
@@ -948,6 +950,8 @@ int t2do_step(t2do_ctx* c, const t2do_params* P, int N, double* uv, int* n, int*
     }
     for (int i = 0; i < N; ++i) { /* separate loop: n_old must stay intact while rows are evaluated above */
         double a = ang[i];
+        if (c->angle_out)
+            c->angle_out[i] = a;
         if (fabs(a - nearbyint(a)) < 1e-9)
             ties_trunc++;
         int avg = (int)a; /* avg_n(i) = mean angle: double -> int truncation */

@@ -1,0 +1,354 @@
+"""GPU parity tests: the CUDA path through the C ABI (lib2dtissue_b200.so) against
+  (1) golden fixtures produced by the UNMODIFIED compiled reference (tests/golden/*.npz),
+  (2) the CPU oracle on fresh seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Bars: bit-exact for every integer/index output (neighbour sets via colour counts + forces, face and vertex
+assignments, headings minus logged truncation ties); fp64 floats within 1e-9 relative (measured: bit-exact);
+fp32 fast path within 1e-4."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import STEP_FIXTURES, golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-9
+TOL32 = 1e-4
+
+
+def make_ctx(t2d, chart, name_or_mode, table=None, **kw):
+    return t2d.Context(chart, table=table, **kw)
+
+
+def rel_err(a, b, scale=None):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    s = np.maximum(np.abs(b), 1.0) if scale is None else scale
+    return float(np.max(np.abs(a - b) / s)) if a.size else 0.0
+
+
+def heading_mismatch_report(n_gpu, n_ref, angle_ref):
+    """Headings must be identical except at truncation ties: the reference's mean angle is within 1e-9 deg of an
+    integer, where the last ulp of atan2 decides.  Returns (#mismatch, #non-tie mismatch)."""
+    bad = np.nonzero(n_gpu != n_ref)[0]
+    non_tie = [i for i in bad if abs(angle_ref[i] - np.rint(angle_ref[i])) >= 1e-9]
+    return len(bad), len(non_tie)
+
+
+def table_for(name, hop_table, metric_tab):
+    if "metric" in name:
+        return metric_tab
+    if "table" in name:
+        return hop_table
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+# single stages against the reference's individual functions
+# ------------------------------------------------------------------------------------------------------
+def test_get_r3d_bit_exact(t2d, chart):
+    g = golden("get_r3d_N4306.npz")
+    ctx = t2d.Context(chart, neigh_mode=t2d.NEIGH_EUCLID, capacity=8192, sigma=0.05)
+    r3d, vid, face = ctx.get_r3d(g["uv"])
+    assert np.array_equal(vid, g["vid"])                      # vertex assignment: bit-exact
+    assert rel_err(r3d, g["r3d"]) <= RTOL64
+    assert np.array_equal(r3d, g["r3d"]), "fp64 lift expected bit-identical (no FMA, same op order)"
+    assert ctx.counters()["locate_fallbacks"] == 0
+
+
+def test_get_r3d_faces_match_oracle(t2d, chart, oracle):
+    rng = np.random.default_rng(5)
+    N = 200000
+    uv = rng.random(2 * N)
+    ctx = t2d.Context(chart, neigh_mode=t2d.NEIGH_EUCLID, capacity=N, sigma=0.05)
+    r3d, vid, face = ctx.get_r3d(uv)
+    r3d_o, vid_o, face_o = oracle.get_r3d(uv)
+    assert np.array_equal(face, face_o) and np.array_equal(vid, vid_o)   # face sets bit-exact
+    assert np.array_equal(r3d, r3d_o)
+
+
+def test_tiling_bit_exact(t2d, chart):
+    k = golden("kat_tiling.npz")
+    ctx = t2d.Context(chart, neigh_mode=t2d.NEIGH_EUCLID, capacity=4096, sigma=0.05)
+    uo, un, nn, fault = ctx.tiling(k["old"], k["new"], k["n"])
+    assert fault == 0
+    assert np.array_equal(nn, k["out_n"])
+    assert np.array_equal(un, k["out_new"]) and np.array_equal(uo, k["out_old"])
+    # the reference's own KAT (tests/simulation/test_EuclideanTiling.cpp:44-72)
+    uo, un, nn, _ = ctx.tiling(k["kat_old"], k["kat_new"], k["kat_n"])
+    assert np.allclose(un, [0.5, 0.7, 0.7, 0.5, 0.8, 0.3], atol=1e-9) and list(nn) == [-280, -60, -48]
+
+
+def test_angles_to_unit_vectors_kat(t2d, chart, oracle_mod):
+    ctx = t2d.Context(chart, neigh_mode=t2d.NEIGH_EUCLID, capacity=8192, sigma=0.05)
+    n = np.array([0, 45, 90, 180, 270, 360], dtype=np.int32)      # tests/simulation/test_LinearAlgebra.cpp:13-40
+    out = ctx.angles_to_unit_vectors(n)
+    exp = np.array([1, np.sqrt(2) / 2, 0, -1, 0, 1, 0, np.sqrt(2) / 2, 1, 0, -1, 0])
+    assert np.allclose(out, exp, atol=1e-9)
+    n = np.arange(-3600, 1080, dtype=np.int32)
+    out = ctx.angles_to_unit_vectors(n)
+    ref = np.zeros(2 * n.size)
+    import ctypes as C
+    oracle_mod.lib().t2do_angles_to_unit_vectors(n.size, n.ctypes.data_as(C.POINTER(C.c_int)),
+                                                 ref.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.array_equal(out, ref)        # host-built libm table: bit-identical to the CPU path
+    assert ctx.counters()["trig_fallbacks"] == 0
+
+
+def test_hop_table_built_on_gpu(t2d, chart):
+    ctx = t2d.Context(chart, table_kind=t2d.TABLE_HOPS_FROM_MESH, neigh_mode=t2d.NEIGH_TABLE, capacity=64)
+    D = ctx.build_hop_table()
+    pins = golden("table_pins.npz")
+    assert hashlib.sha256(D.tobytes()).hexdigest() == str(pins["sha256"])   # == the reference's table
+
+
+# ------------------------------------------------------------------------------------------------------
+# the full step against the compiled reference's golden outputs
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", STEP_FIXTURES)
+def test_step_fp64_vs_reference_golden(t2d, chart, oracle, hop_table, metric_tab, name):
+    z = golden(name + ".npz")
+    v0, k, sigma, h = (float(x) for x in z["params"])
+    mode = int(z["mode"])
+    tab = table_for(name, hop_table, metric_tab)
+    if tab is not None:
+        oracle.set_table(tab.astype(np.float64) if tab.dtype != np.uint8 else tab)
+    N = z["n0"].size
+    ctx = t2d.Context(chart, table=tab, v0=v0, k=k, sigma=sigma, step_size=h, neigh_mode=mode,
+                      precision=t2d.PRECISION_FP64, capacity=N)
+    total_bad = 0
+    for s in range(1, int(z["nsteps"]) + 1):
+        p = s - 1
+        uv, n, vid, r3d = z["uv%d" % p], z["n%d" % p], z["vid%d" % p], z["r3d%d" % p]
+        ctx.set_state(uv, n, vid, r3d)
+        F, nh, col = ctx.forces()
+        assert np.array_equal(col, z["color%d" % s]), "neighbour counts (0 != d <= 2.4 sigma) must be bit-exact"
+        fscale = np.maximum(np.abs(z["F%d" % s]), 1.0)
+        assert rel_err(F, z["F%d" % s], fscale) <= RTOL64
+        ctx.set_state(uv, n, vid, r3d)
+        fault = ctx.step(1)
+        out = ctx.download()
+        assert fault == int(z["fault%d" % s])
+        has_noise = ("eta%d" % s) in z.files
+        # the oracle (bit-identical to the reference, test_oracle_vs_reference.py) gives the pre-truncation angle
+        o = oracle.step(uv, n, vid, r3d, v0, k, sigma, h, mode=mode)
+        if not has_noise:
+            nbad, nontie = heading_mismatch_report(nh, o["n"], o["angle"])
+            assert nontie == 0, "heading differs away from a truncation tie"
+            total_bad += nbad
+        good = (nh == o["n"]) if not has_noise else np.ones(N, dtype=bool)
+        # particles whose heading matched must match the reference everywhere else, bit-exact on indices
+        ref_uv, ref_vid, ref_r3d = o["uv"], o["vid"], o["r3d"]
+        g2 = np.concatenate([good, good])
+        g3 = np.concatenate([good, good, good])
+        assert np.array_equal(out["vid"][good], ref_vid[good])
+        assert rel_err(out["rdot"], o["rdot"], np.maximum(np.abs(o["rdot"]), 1.0)) <= RTOL64
+        assert rel_err(out["uv"][g2], ref_uv[g2]) <= RTOL64
+        assert rel_err(out["r3d"][g3], ref_r3d[g3]) <= RTOL64
+        assert np.array_equal(out["color"], z["color%d" % s])
+        if not has_noise:
+            assert np.array_equal(out["rdot"], z["rdot%d" % s]), "fp64 velocities expected bit-identical"
+            assert np.array_equal(out["uv"][g2], z["uv%d" % s][g2])
+            assert np.array_equal(out["r3d"][g3], z["r3d%d" % s][g3])
+    c = ctx.counters()
+    assert c["order_fallbacks"] == 0 and c["trig_fallbacks"] == 0 and c["locate_fallbacks"] == 0
+    assert total_bad <= 0.02 * N * int(z["nsteps"]), "too many truncation-tie mismatches"
+    print("%s: heading tie mismatches %d / %d, counters %s" % (name, total_bad, N * int(z["nsteps"]), c))
+
+
+@pytest.mark.parametrize("name", ["step_table_wide_N1500", "step_metric_N1500", "step_euclid_N2000",
+                                  "step_euclid_dense_N1500"])
+def test_step_fp32_fast_path(t2d, chart, hop_table, metric_tab, name):
+    z = golden(name + ".npz")
+    v0, k, sigma, h = (float(x) for x in z["params"])
+    mode = int(z["mode"])
+    tab = table_for(name, hop_table, metric_tab)
+    N = z["n0"].size
+    ctx = t2d.Context(chart, table=tab, v0=v0, k=k, sigma=sigma, step_size=h, neigh_mode=mode,
+                      precision=t2d.PRECISION_FP32, capacity=N)
+    ctx.set_state(z["uv0"], z["n0"], z["vid0"], z["r3d0"])
+    F, nh, col = ctx.forces()
+    # neighbour sets: table mode compares in the table's stored type -> exact; Euclid mode may differ at the cutoff
+    if mode == 0:
+        assert np.array_equal(col, z["color1"])
+    else:
+        assert np.mean(col != z["color1"]) < 0.01
+    ctx.set_state(z["uv0"], z["n0"], z["vid0"], z["r3d0"])
+    ctx.step(1)
+    out = ctx.download()
+    speed = np.hypot(z["rdot1"][:N], z["rdot1"][N:])
+    ok = np.abs(nh - z["n1"]) <= 1
+    assert ok.mean() > 0.97
+    sc = np.maximum(np.concatenate([speed, speed]), 1.0)
+    assert rel_err(out["rdot"], z["rdot1"], sc) <= 20 * TOL32     # |F| sums of ~1e3-magnitude terms in fp32
+    # positions: compare particles that did not wrap differently
+    d = np.abs(out["uv"] - z["uv1"])
+    close = (d[:N] < 1e-3) & (d[N:] < 1e-3)
+    assert close.mean() > 0.97
+    assert np.max(d[np.concatenate([close, close])]) <= 50 * TOL32 * max(1.0, float(speed.max()) * h)
+    same_vid = out["vid"] == z["vid1"]
+    assert same_vid[close].mean() > 0.98
+
+
+# ------------------------------------------------------------------------------------------------------
+# fresh seeded inputs against the oracle, larger N
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,N,sigma", [(1, 30000, None), (0, 20000, 0.4166666666666667), (0, 6000, 1.3)])
+def test_step_vs_oracle_seeded(t2d, chart, oracle, hop_table, mode, N, sigma):
+    uv, n = t2d.seed_particles(N, seed=77 + N)
+    if sigma is None:
+        sigma = float(np.sqrt(0.5 * 451.3 / (np.pi * N)))
+    tab = hop_table if mode == 0 else None
+    if mode == 0:
+        oracle.set_table(hop_table)
+    ctx = t2d.Context(chart, table=tab, v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=mode, capacity=N)
+    ctx.set_particles(uv, n)
+    s0 = ctx.download()
+    r3d_o, vid_o, _ = oracle.get_r3d(uv)
+    assert np.array_equal(s0["vid"], vid_o) and np.array_equal(s0["r3d"], r3d_o)
+    uv_c, n_c, vid_c, r3d_c = uv, n, vid_o, r3d_o
+    for step in range(3):
+        o = oracle.step(uv_c, n_c, vid_c, r3d_c, 0.1, 1.0, sigma, 0.001, mode=mode)
+        ctx.set_state(uv_c, n_c, vid_c, r3d_c)
+        fault = ctx.step(1)
+        g = ctx.download()
+        assert fault == o["fault"]
+        nbad, nontie = heading_mismatch_report(g["n"], o["n"], o["angle"])
+        assert nontie == 0 and nbad <= 0.02 * N
+        assert np.array_equal(g["color"], o["color"])
+        assert np.array_equal(g["rdot"], o["rdot"])
+        good = g["n"] == o["n"]
+        assert np.array_equal(g["vid"][good], o["vid"][good]) and np.array_equal(g["face"][good], o["face"][good])
+        assert np.array_equal(g["uv"][np.concatenate([good, good])], o["uv"][np.concatenate([good, good])])
+        uv_c, n_c, vid_c, r3d_c = o["uv"], o["n"], o["vid"], o["r3d"]
+    c = ctx.counters()
+    assert c["pairs_in_range"] > 0 and c["order_fallbacks"] == 0
+
+
+def test_noise_parity_with_oracle(t2d, chart, oracle):
+    N, sigma, eta, seed = 5000, 0.1, 0.2, 424242
+    uv, n = t2d.seed_particles(N, seed=5)
+    ctx = t2d.Context(chart, v0=0.1, k=1.0, sigma=sigma, step_size=0.001, eta=eta, seed=seed,
+                      neigh_mode=t2d.NEIGH_EUCLID, capacity=N)
+    ctx.set_particles(uv, n)
+    s0 = ctx.download()
+    ctx.step_index = 17
+    ctx.step(1)
+    g = ctx.download()
+    o = oracle.step(uv, n, s0["vid"], s0["r3d"], 0.1, 1.0, sigma, 0.001, eta=eta, seed=seed, mode=1, step_index=17)
+    # identical Philox stream on both sides -> identical noisy headings except where the noiseless mean angle ties
+    bad = np.nonzero(g["n"] != o["n"])[0]
+    assert all(abs(o["angle"][i] - np.rint(o["angle"][i])) < 1e-9 for i in bad) and len(bad) <= 0.02 * N
+    assert len(np.unique(g["n"] - n)) > 50      # the noise really is per particle
+
+
+def test_step_host_is_the_dropin(t2d, chart, hop_table):
+    z = golden("step_table_dense_N1500.npz")
+    v0, k, sigma, h = (float(x) for x in z["params"])
+    N = z["n0"].size
+    ctx = t2d.Context(chart, table=hop_table, v0=v0, k=k, sigma=sigma, step_size=h, neigh_mode=0, capacity=N)
+    uv, n, vid, r3d = z["uv0"].copy(), z["n0"].copy(), z["vid0"].copy(), z["r3d0"].copy()
+    rdot, color = np.zeros(2 * N), np.zeros(N, dtype=np.int32)
+    fault = ctx.step_host(uv, n, vid, r3d, rdot, color)
+    assert fault == int(z["fault1"])
+    assert np.array_equal(color, z["color1"]) and np.array_equal(rdot, z["rdot1"])
+    good = n == z["n1"]
+    assert good.mean() > 0.98
+    assert np.array_equal(vid[good], z["vid1"][good])
+
+
+def test_upload_order_independence(t2d, chart, hop_table):
+    """Results are a function of (id -> state), not of device order or upload order."""
+    N = 4000
+    uv, n = t2d.seed_particles(N, seed=9)
+    ctx = t2d.Context(chart, sigma=0.08, neigh_mode=t2d.NEIGH_EUCLID, capacity=N)
+    ctx.set_particles(uv, n)
+    ctx.step(2)
+    a = ctx.download()
+    perm = np.random.default_rng(1).permutation(N)
+    uvp = np.concatenate([uv[:N][perm], uv[N:][perm]])
+    ctx.set_particles(uvp, n[perm], ids=perm.astype(np.uint32))
+    ctx.step_index = 0
+    ctx.step(2)
+    b = ctx.download()
+    assert np.array_equal(b["n"], a["n"][perm]) and np.array_equal(b["uv"][:N], a["uv"][:N][perm])
+    assert np.array_equal(b["color"], a["color"][perm])
+
+
+def test_driver_mirror_readme_config(t2d, chart, oracle, hop_table):
+    """BASELINE.json configs[0]: 100 particles, 50 steps, v0 = 0.02 (README run), driven through the Tissue2D mirror
+    of `_2DTissue`; the oracle is chained beside it and re-synchronised at truncation ties."""
+    N, steps = 100, 50
+    uv, n = t2d.seed_particles(N, seed=1234)
+    sim = t2d.Tissue2D(chart=chart, particle_count=N, step_count=steps, v0=0.02, table=hop_table)
+    sim.start(uv, n)
+    oracle.set_table(hop_table)
+    s = sim.ctx.download()
+    st = dict(uv=uv, n=n, vid=s["vid"], r3d=s["r3d"])
+    ties = 0
+    while not sim.is_finished():
+        system = sim.update()
+        o = oracle.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.02, 1.0, 0.4166666666666667, 0.001, mode=0)
+        g = sim.ctx.download()
+        nbad, nontie = heading_mismatch_report(g["n"], o["n"], o["angle"])
+        assert nontie == 0
+        ties += nbad
+        good = g["n"] == o["n"]
+        assert np.array_equal(g["uv"][np.concatenate([good, good])], o["uv"][np.concatenate([good, good])])
+        phi_o = oracle.observables(g["n"], g["rdot"])[0]
+        assert abs(system.order_parameter - phi_o) < 1e-12
+        st = dict(uv=g["uv"], n=g["n"], vid=g["vid"], r3d=g["r3d"])      # follow the GPU trajectory
+    assert len(sim.get_order_parameter()) == steps and ties <= 0.02 * N * steps
+
+
+# ------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", [0, 1])
+def test_full_size_properties_1M(t2d, chart, precision):
+    N = 1_000_000
+    uv, n = t2d.seed_particles(N, seed=1234)
+    sigma = float(np.sqrt(0.5 * 451.3 / (np.pi * N)))
+    ctx = t2d.Context(chart, sigma=sigma, neigh_mode=t2d.NEIGH_EUCLID, precision=precision, capacity=N)
+    ctx.set_particles(uv, n)
+    s0 = ctx.download()
+    # idempotence of the projection: projecting the same uv again reproduces face / vertex / 3-D point
+    r3d, vid, face = ctx.get_r3d(uv)
+    if precision == 0:
+        assert np.array_equal(vid, s0["vid"]) and np.array_equal(face, s0["face"]) and np.array_equal(r3d, s0["r3d"])
+    fault = ctx.step(5)
+    assert fault == 0
+    s = ctx.download()
+    assert np.all((s["uv"] >= 0) & (s["uv"] <= 1))                           # nobody lost (Validation.cpp:66-72)
+    assert np.all(np.isfinite(s["uv"])) and np.all(np.isfinite(s["r3d"]))
+    assert np.all((s["n"] >= -270 * 3) & (s["n"] < 360))
+    assert np.all((s["vid"] >= 0) & (s["vid"] < ctx.V)) and np.all((s["face"] >= 0) & (s["face"] < ctx.F))
+    # the lifted point lies in the bounding box of its face's corners, and the stored vertex is a corner
+    faces, x3d = chart["faces"], chart["x3d"]
+    corners = x3d[faces[s["face"]]]                                         # N x 3 x 3
+    P = np.stack([s["r3d"][:N], s["r3d"][N:2 * N], s["r3d"][2 * N:]], 1)
+    tol = 1e-9 if precision == 0 else 1e-4
+    assert np.all(P >= corners.min(1) - tol) and np.all(P <= corners.max(1) + tol)
+    assert np.all((faces[s["face"]] == s["vid"][:, None]).any(1))
+    # colour counts are symmetric-relation degrees: their sum is even
+    assert int(s["color"].sum()) % 2 == 0
+    obs = ctx.observables()
+    assert 0 <= obs["phi"] <= 1 and obs["mean_speed"] >= 0.1 - 1e-6
+    c = ctx.counters()
+    assert c["wrap_cap_hits"] == 0 and c["locate_fallbacks"] == 0
+
+
+def test_table_mode_1M_hop_table_runs(t2d, chart, hop_table):
+    """BASELINE.json configs[2] shape: 1M particles, table criterion (the reference's stock hop-count table)."""
+    N = 1_000_000
+    uv, n = t2d.seed_particles(N, seed=4321)
+    ctx = t2d.Context(chart, table=hop_table, neigh_mode=t2d.NEIGH_TABLE, precision=t2d.PRECISION_FP32, capacity=N)
+    ctx.set_particles(uv, n)
+    fault = ctx.step(1)
+    s = ctx.download(("uv", "n", "vid", "color"))
+    assert fault in (0,)
+    assert np.all((s["uv"] >= 0) & (s["uv"] <= 1))
+    # in table mode all particles of one vertex bucket share one neighbour set -> one colour value per bucket
+    s0 = ctx.download(("vid",))
+    assert ctx.counters()["pairs_in_range"] > N
