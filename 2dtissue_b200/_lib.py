@@ -27,8 +27,8 @@ class Params(C.Structure):
 
 class Counters(C.Structure):
     _names = ("steps", "kernel_launches", "pairs_in_range", "ties_cutoff", "ties_trunc", "wraps", "wrap_cap_hits",
-              "order_fallbacks", "trig_fallbacks", "locate_fallbacks", "max_row")
-    _fields_ = [(k, C.c_int64) for k in _names] + [("reserved", C.c_int64 * 5)]
+              "order_fallbacks", "trig_fallbacks", "locate_fallbacks", "max_row", "cell_fallbacks", "buckets")
+    _fields_ = [(k, C.c_int64) for k in _names] + [("reserved", C.c_int64 * 3)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k in self._names}

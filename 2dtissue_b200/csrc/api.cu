@@ -130,12 +130,15 @@ template <typename R> class Engine : public EngineBase {
   private:
     void upload_chart();
     void build_csr();
+    void build_vox();
+    void alloc_buckets(int nbuckets);
     void build_hop_table_device(std::vector<uint8_t>* host_out);
     void apply_params();
+    void resort(bool keys_ready);
     void one_step(bool moving, cudaEvent_t* ev, int* nev);
     int read_fault();
     void ingest(int N, const double* uv, const int* heading, const int* vid, const double* r3d, const uint32_t* ids,
-                ParticleArrays<R>& dst, bool separate_origin);
+                ParticleArrays<R>& dst);
 
     int device_ = 0, sm_count_ = 148;
     cudaStream_t stream_ = nullptr;
@@ -143,7 +146,8 @@ template <typename R> class Engine : public EngineBase {
     t2d_params P_;
     HostChart chart_;
     int capacity_ = 0;
-    bool have_ids_ = false;
+    bool sorted_ = false;   // `cur` is in bucket order and start[] is valid
+    double vox_sigma_ = -1, vox_color_ = -1;
     int64_t launches_ = 0, steps_ = 0;
 
     // chart
@@ -152,16 +156,17 @@ template <typename R> class Engine : public EngineBase {
     DevBuf<Pos3<R>> d_x3d_;
     DevBuf<int> d_gstart_, d_gfaces_;
     DevBuf<double2> d_trig_d_;
-    DevBuf<float2> d_trig_f_;
+    DevBuf<CrEntry> d_cr_;
+    DevBuf<uint4> d_vox_blocks_;
     DevBuf<int> d_csr_start_, d_csr_col_;
     DevBuf<double> d_csr_d_;
     DevBuf<int> d_adj_start_, d_adj_;
     // particles
-    DevBuf<Real2<R>> d_uv_[2], d_uv_new_, d_rdot_, d_F_;
-    DevBuf<int2> d_hv_[2];
-    DevBuf<Pos3<R>> d_X_[2];
-    DevBuf<int> d_face_[2], d_new_heading_, d_color_;
-    DevBuf<uint32_t> d_id_[2], d_origin_[2], d_key_, d_rank_;
+    DevBuf<Real2<R>> d_uv_[2], d_rdot_[2], d_uv_new_, d_F_;
+    DevBuf<Pos3<R>> d_pos_[2];
+    DevBuf<int4> d_aux_[2];
+    DevBuf<int> d_color_[2], d_new_heading_;
+    DevBuf<uint32_t> d_key_, d_rank_;
     DevBuf<int> d_count_, d_start_, d_blocksums_, d_work_;
     DevBuf<DevCounters> d_counters_;
     DevBuf<double> d_obs_;
@@ -220,22 +225,17 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     // particle storage
     const size_t C = (size_t)capacity_;
     for (int b = 0; b < 2; ++b) {
+        d_pos_[b].alloc(C);
         d_uv_[b].alloc(C);
-        d_hv_[b].alloc(C);
-        d_X_[b].alloc(C);
-        d_face_[b].alloc(C);
-        d_id_[b].alloc(C);
-        d_origin_[b].alloc(C);
+        d_aux_[b].alloc(C);
+        d_rdot_[b].alloc(C);
+        d_color_[b].alloc(C);
     }
     d_uv_new_.alloc(C);
-    d_rdot_.alloc(C);
     d_F_.alloc(C);
     d_new_heading_.alloc(C);
-    d_color_.alloc(C);
     d_key_.alloc(C);
     d_rank_.alloc(C);
-    CK(cudaMemsetAsync(d_rdot_.p, 0, C * sizeof(Real2<R>), stream_));
-    CK(cudaMemsetAsync(d_color_.p, 0, C * sizeof(int), stream_));
     d_counters_.alloc(1);
     CK(cudaMemsetAsync(d_counters_.p, 0, sizeof(DevCounters), stream_));
     d_obs_.alloc(T2D_OBS_LEN);
@@ -243,35 +243,16 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     d_stage_in_.alloc(C * (16 + 4 + 4 + 24 + 4) + 256);
     d_stage_out_.alloc(C * (16 + 4 + 4 + 24 + 16 + 4 + 4 + 16 + 4) + 256);
 
-    int M;
-    if (P_.neigh_mode == T2D_NEIGH_TABLE) {
-        M = chart_.V;
-    } else {
-        M = 1024;
-        while ((size_t)M < 2 * C) M <<= 1;
-    }
-    A_.M = M;
-    A_.hash_mask = (uint32_t)(M - 1);
-    d_count_.alloc((size_t)M + 8);
-    d_start_.alloc((size_t)M + 8);
-    d_blocksums_.alloc((size_t)scan_blocks(M) + 8);
-    CK(cudaMemsetAsync(d_count_.p, 0, ((size_t)M + 8) * sizeof(int), stream_));
-
-    A_.cur = {d_uv_[0].p, d_hv_[0].p, d_X_[0].p, d_face_[0].p, d_id_[0].p, d_id_[0].p};
-    A_.alt = {d_uv_[1].p, d_hv_[1].p, d_X_[1].p, d_face_[1].p, d_id_[1].p, d_id_[1].p};
+    A_.cur = {d_pos_[0].p, d_uv_[0].p, d_aux_[0].p, d_rdot_[0].p, d_color_[0].p};
+    A_.alt = {d_pos_[1].p, d_uv_[1].p, d_aux_[1].p, d_rdot_[1].p, d_color_[1].p};
     A_.key = d_key_.p;
     A_.rank = d_rank_.p;
-    A_.count = d_count_.p;
-    A_.start = d_start_.p;
-    A_.blocksums = d_blocksums_.p;
     A_.uv_new = d_uv_new_.p;
-    A_.rdot = d_rdot_.p;
     A_.F = d_F_.p;
     A_.new_heading = d_new_heading_.p;
-    A_.color = d_color_.p;
     A_.counters = d_counters_.p;
     A_.trig_d = d_trig_d_.p;
-    A_.trig_f = d_trig_f_.p;
+    A_.cr = d_cr_.p;
     A_.work_counter = d_work_.p;
     A_.mode = P_.neigh_mode;
     A_.write_F = 0;
@@ -312,7 +293,6 @@ template <typename R> void Engine<R>::upload_chart()
         x3[v].w = R(0);
         for (int k = 0; k < 3; ++k) mn[k] = std::min(mn[k], chart_.x3d[3 * (size_t)v + k]);
     }
-    for (int k = 0; k < 3; ++k) A_.mesh.eucl_origin[k] = (R)mn[k];   // shifted by one cell in apply_params
     d_tri_.upload(tri, stream_);
     d_tri_vid_.upload(tv, stream_);
     d_x3d_.upload(x3, stream_);
@@ -369,15 +349,14 @@ template <typename R> void Engine<R>::upload_chart()
     // cos/sin of integer degrees exactly as the reference's libm call sees them:
     // cos(double(n) * DEG_TO_RAD), LinearAlgebra.cpp:37-41, OrientationHelper.cpp:96-100
     std::vector<double2> td(TRIG_N);
-    std::vector<float2> tf(TRIG_N);
     for (int q = 0; q < TRIG_N; ++q) {
         double angle_degrees = (double)(TRIG_MIN + q);
         double angle_radians = angle_degrees * DEG_TO_RAD_D;
         td[q] = make_double2(cos(angle_radians), sin(angle_radians));
-        tf[q] = make_float2((float)td[q].x, (float)td[q].y);
     }
     d_trig_d_.upload(td, stream_);
-    d_trig_f_.upload(tf, stream_);
+    std::vector<CrEntry> cr(kCrTable, kCrTable + 181);
+    d_cr_.upload(cr, stream_);
 
     // vertex adjacency (both directions of every face edge; duplicates are harmless for BFS)
     std::vector<int> deg((size_t)V + 1, 0);
@@ -445,6 +424,102 @@ template <typename R> void Engine<R>::build_csr()
     A_.csr.d = d_csr_d_.p;
 }
 
+template <typename R> void Engine<R>::alloc_buckets(int nbuckets)
+{
+    A_.M = nbuckets;
+    if (d_count_.n < (size_t)nbuckets + 8) {
+        d_count_.alloc((size_t)nbuckets + 8);
+        d_start_.alloc((size_t)nbuckets + 8);
+        d_blocksums_.alloc((size_t)scan_blocks(nbuckets) + 8);
+    }
+    CK(cudaMemsetAsync(d_count_.p, 0, d_count_.n * sizeof(int), stream_));
+    A_.count = d_count_.p;
+    A_.start = d_start_.p;
+    A_.blocksums = d_blocksums_.p;
+}
+
+// Sparse voxel index of the 3-D cell list (t2d_internal.h DevVox).  Cell edge = 2*rmax*(1+margin); the cells a
+// particle can ever occupy are those the mesh surface touches (positions are convex combinations of a face's
+// corners, CellHelper.cpp:143-146), found by a GPU voxelisation; blocks are numbered along a Morton curve.
+template <typename R> void Engine<R>::build_vox()
+{
+    const double two_sigma = 2 * P_.sigma, color_r = P_.color_factor * P_.sigma;
+    const double rmax = std::max(two_sigma, color_r);
+    const double margin = sizeof(R) == 8 ? 1e-9 : 1e-3;
+    const double cs = 2.0 * rmax * (1.0 + margin);
+    if (!(cs > 0)) throw CudaError{"sigma must be positive"};
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int v = 0; v < chart_.V; ++v)
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = std::min(mn[k], chart_.x3d[3 * (size_t)v + k]);
+            mx[k] = std::max(mx[k], chart_.x3d[3 * (size_t)v + k]);
+        }
+    double org[3];
+    int nc[3], nb[3];
+    double extent = 0;
+    for (int k = 0; k < 3; ++k) {
+        org[k] = mn[k] - 2.0 * cs;
+        double n = std::floor((mx[k] - org[k]) / cs) + 3.0;
+        if (n > 2.0e9) throw CudaError{"sigma is too small for the mesh extent (cell grid axis overflows)"};
+        nc[k] = (int)n;
+        nb[k] = (nc[k] + 3) / 4;
+        extent = std::max(extent, mx[k] - mn[k]);
+    }
+    const double nblocks_d = (double)nb[0] * nb[1] * nb[2];
+    if (nblocks_d > 4.0e8) throw CudaError{"sigma is too small for the mesh extent (the block table of the cell list would exceed 6 GB)"};
+    const size_t nblocks = (size_t)nblocks_d;
+    const double reach = 0.5 * std::sqrt(3.0) * cs + 0.02 * cs + 2e-5 * extent;
+
+    DevBuf<unsigned long long> d_occ;
+    d_occ.alloc(nblocks);
+    CK(cudaMemsetAsync(d_occ.p, 0, nblocks * sizeof(unsigned long long), stream_));
+    Launch<R>::voxelize(A_.mesh, org, cs, reach, nc, nb[0], nb[1], d_occ.p, stream_);
+    launches_++;
+    std::vector<unsigned long long> occ(nblocks);
+    CK(cudaMemcpyAsync(occ.data(), d_occ.p, nblocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+
+    // occupied blocks in Morton order -> compact base index
+    auto spread = [](uint64_t v) {   // 21 bits -> every third bit
+        v &= 0x1fffffull;
+        v = (v | v << 32) & 0x1f00000000ffffull;
+        v = (v | v << 16) & 0x1f0000ff0000ffull;
+        v = (v | v << 8) & 0x100f00f00f00f00full;
+        v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+        v = (v | v << 2) & 0x1249249249249249ull;
+        return v;
+    };
+    std::vector<std::pair<uint64_t, size_t>> order;
+    for (size_t b = 0; b < nblocks; ++b)
+        if (occ[b]) {
+            size_t bx = b % nb[0], by = (b / nb[0]) % nb[1], bz = b / ((size_t)nb[0] * nb[1]);
+            order.emplace_back(spread(bx) | (spread(by) << 1) | (spread(bz) << 2), b);
+        }
+    std::sort(order.begin(), order.end());
+    std::vector<uint4> blocks(nblocks, make_uint4(0, 0, 0, 0));
+    long long base = 0;
+    for (auto& o : order) {
+        unsigned long long w = occ[o.second];
+        blocks[o.second] = make_uint4((unsigned)w, (unsigned)(w >> 32), (unsigned)base, 0);
+        base += __builtin_popcountll(w);
+    }
+    if (base > 2000000000LL) throw CudaError{"cell list too large"};
+    d_vox_blocks_.upload(blocks, stream_);
+    CK(cudaStreamSynchronize(stream_));
+    A_.vox.ncx = nc[0];
+    A_.vox.ncy = nc[1];
+    A_.vox.ncz = nc[2];
+    A_.vox.nbx = nb[0];
+    A_.vox.nby = nb[1];
+    A_.vox.nbz = nb[2];
+    A_.vox.M = (int)base;
+    A_.vox.blocks = d_vox_blocks_.p;
+    for (int k = 0; k < 3; ++k) A_.vox.origin[k] = (R)org[k];
+    A_.vox.inv_cell = (R)(1.0 / cs);
+    alloc_buckets((int)base + 1);   // + the overflow bucket
+}
+
 template <typename R> void Engine<R>::apply_params()
 {
     A_.v0 = (R)P_.v0;
@@ -459,18 +534,16 @@ template <typename R> void Engine<R>::apply_params()
     A_.eta360 = P_.eta * 360.0;
     A_.seed = P_.seed;
     if (P_.neigh_mode == T2D_NEIGH_EUCLID) {
-        const double rmax = std::max(two_sigma, color_r);
-        const double margin = sizeof(R) == 8 ? 1e-9 : 1e-3;
-        const double cs = 2.0 * rmax * (1.0 + margin);
-        if (!(cs > 0)) throw CudaError{"sigma must be positive"};
-        A_.cell_size = (R)cs;
-        A_.inv_cell = (R)(1.0 / cs);
-        double mn[3] = {1e300, 1e300, 1e300};
-        for (int v = 0; v < chart_.V; ++v)
-            for (int k = 0; k < 3; ++k) mn[k] = std::min(mn[k], chart_.x3d[3 * (size_t)v + k]);
-        for (int k = 0; k < 3; ++k) A_.mesh.eucl_origin[k] = (R)(mn[k] - 2.0 * cs);
+        if (vox_sigma_ != P_.sigma || vox_color_ != P_.color_factor) {
+            build_vox();
+            vox_sigma_ = P_.sigma;
+            vox_color_ = P_.color_factor;
+            sorted_ = false;
+        }
     } else {
         build_csr();
+        alloc_buckets(chart_.V);
+        sorted_ = false;
     }
 }
 
@@ -486,7 +559,7 @@ template <typename R> int Engine<R>::set_params(const t2d_params* p)
 
 template <typename R>
 void Engine<R>::ingest(int N, const double* uv, const int* heading, const int* vid, const double* r3d, const uint32_t* ids,
-                       ParticleArrays<R>& dst, bool separate_origin)
+                       ParticleArrays<R>& dst)
 {
     // raw host arrays -> device staging (sizes of the reference's own arrays) -> SoA conversion on the device
     unsigned char* base = d_stage_in_.p;
@@ -503,9 +576,23 @@ void Engine<R>::ingest(int N, const double* uv, const int* heading, const int* v
     in.vid = vid ? (const int*)put(vid, sizeof(int) * (size_t)N) : nullptr;
     in.r3d = r3d ? (const double*)put(r3d, sizeof(double) * 3 * (size_t)N) : nullptr;
     in.ids = ids ? (const uint32_t*)put(ids, sizeof(uint32_t) * (size_t)N) : nullptr;
-    (void)separate_origin;
     IoLaunch<R>::ingest(N, in, dst, stream_);
     launches_++;
+}
+
+// counting sort of `cur` into bucket order (cur -> alt, then swap); keys_ready: the producing kernel already
+// wrote key / rank / histogram
+template <typename R> void Engine<R>::resort(bool keys_ready)
+{
+    if (!keys_ready) {
+        Launch<R>::bin(A_, stream_);
+        launches_++;
+    }
+    launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
+    Launch<R>::scatter(A_, stream_);
+    std::swap(A_.cur, A_.alt);
+    launches_ += 4;
+    sorted_ = true;
 }
 
 template <typename R>
@@ -520,19 +607,14 @@ int Engine<R>::set_state(int N, const double* uv, const int* heading, const int*
     CK(cudaSetDevice(device_));
     this->N = N;
     A_.N = N;
-    have_ids_ = ids != nullptr;
-    // index buffers: with caller ids the upload position travels separately, otherwise origin aliases id
-    const int cb = (A_.cur.uv == d_uv_[0].p) ? 0 : 1;
-    A_.cur.origin = have_ids_ ? d_origin_[cb].p : A_.cur.id;
-    A_.alt.origin = have_ids_ ? d_origin_[1 - cb].p : A_.alt.id;
-    ingest(N, uv, heading, vid, r3d, ids, A_.cur, have_ids_);
+    ingest(N, uv, heading, vid, r3d, ids, A_.cur);
     if (project) {
         Launch<R>::project_only(A_, stream_);
         launches_++;
     }
-    CK(cudaMemsetAsync(d_rdot_.p, 0, (size_t)std::max(N, 1) * sizeof(Real2<R>), stream_));
-    CK(cudaMemsetAsync(d_color_.p, 0, (size_t)std::max(N, 1) * sizeof(int), stream_));
+    resort(false);
     CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -555,7 +637,7 @@ template <typename R> int Engine<R>::download(double* uv, int* heading, int* vid
     if (rdot) o.rdot = (double*)take(16 * N);
     if (color) o.color = (int*)take(4 * N);
     if (face) o.face = (int*)take(4 * N);
-    IoLaunch<R>::egest((int)N, A_.cur, A_.rdot, A_.color, A_.F, A_.new_heading, o, stream_);
+    IoLaunch<R>::egest((int)N, A_.cur, A_.F, A_.new_heading, o, stream_);
     launches_++;
     if (uv) CK(cudaMemcpyAsync(uv, o.uv, 16 * N, cudaMemcpyDeviceToHost, stream_));
     if (heading) CK(cudaMemcpyAsync(heading, o.heading, 4 * N, cudaMemcpyDeviceToHost, stream_));
@@ -573,23 +655,30 @@ template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int
     auto mark = [&]() {
         if (ev) CK(cudaEventRecord(ev[(*nev)++], stream_));
     };
+    if (!sorted_) resort(false);
     A_.step = (uint64_t)step_index;
     mark();
-    Launch<R>::count_keys(A_, stream_);
-    mark();
-    launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
-    mark();
-    Launch<R>::reorder(A_, stream_);
-    std::swap(A_.cur, A_.alt);
-    mark();
-    if (P_.neigh_mode == T2D_NEIGH_TABLE)
+    if (P_.neigh_mode == T2D_NEIGH_EUCLID) {
+        Launch<R>::step_euclid(A_, moving, stream_);   // cur -> alt (+ next keys)
+        launches_++;
+        mark();
+        if (moving) std::swap(A_.cur, A_.alt);
+    } else {
         Launch<R>::neigh_table(A_, stream_, sm_count_);
-    else
-        Launch<R>::neigh_euclid(A_, stream_);
-    mark();
-    launches_ += 6;
+        launches_++;
+        mark();
+        if (moving) {
+            Launch<R>::wrap_project(A_, stream_);   // in place (+ next keys)
+            launches_++;
+            mark();
+        }
+    }
     if (moving) {
-        Launch<R>::wrap_project(A_, stream_);
+        launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
+        launches_ += 3;
+        mark();
+        Launch<R>::scatter(A_, stream_);
+        std::swap(A_.cur, A_.alt);
         launches_++;
         mark();
         step_index++;
@@ -650,7 +739,7 @@ template <typename R> int Engine<R>::forces(double* F, int* new_heading, int* co
     o.new_heading = (int*)(base + off);
     off += (4 * N + 15) & ~(size_t)15;
     o.color = (int*)(base + off);
-    IoLaunch<R>::egest((int)N, A_.cur, A_.rdot, A_.color, A_.F, A_.new_heading, o, stream_);
+    IoLaunch<R>::egest((int)N, A_.cur, A_.F, A_.new_heading, o, stream_);
     launches_++;
     if (F) CK(cudaMemcpyAsync(F, o.F, 16 * N, cudaMemcpyDeviceToHost, stream_));
     if (new_heading) CK(cudaMemcpyAsync(new_heading, o.new_heading, 4 * N, cudaMemcpyDeviceToHost, stream_));
@@ -663,7 +752,7 @@ template <typename R> int Engine<R>::forces(double* F, int* new_heading, int* co
 template <typename R> int Engine<R>::observables(double* out)
 {
     CK(cudaSetDevice(device_));
-    launch_observables(A_.cur.hv, A_.rdot, sizeof(R) == 4, this->N, d_trig_d_.p, d_obs_.p, stream_);
+    launch_observables(A_.cur.pos, A_.cur.rdot, sizeof(R) == 4, this->N, d_trig_d_.p, d_obs_.p, stream_);
     launches_++;
     double h[T2D_OBS_LEN];
     CK(cudaMemcpyAsync(h, d_obs_.p, sizeof(h), cudaMemcpyDeviceToHost, stream_));
@@ -698,6 +787,8 @@ template <typename R> int Engine<R>::get_counters(t2d_counters* out)
     out->trig_fallbacks = (int64_t)c.trig_fallbacks;
     out->locate_fallbacks = (int64_t)c.locate_fallbacks;
     out->max_row = (int64_t)c.max_row;
+    out->cell_fallbacks = (int64_t)c.cell_fallbacks;
+    out->buckets = A_.M;
     return 0;
 }
 
@@ -719,8 +810,7 @@ template <typename R> int Engine<R>::get_r3d(int N, const double* uv, double* r3
     StepArgs<R> T = A_;
     T.N = N;
     T.cur = A_.alt;
-    T.cur.origin = T.cur.id;
-    ingest(N, uv, nullptr, nullptr, nullptr, nullptr, T.cur, false);
+    ingest(N, uv, nullptr, nullptr, nullptr, nullptr, T.cur);
     Launch<R>::project_only(T, stream_);
     launches_++;
     HostViewOut o{};
@@ -728,7 +818,7 @@ template <typename R> int Engine<R>::get_r3d(int N, const double* uv, double* r3
     o.r3d = (double*)base;
     o.vid = (int*)(base + 24 * (size_t)N);
     o.face = (int*)(base + 24 * (size_t)N + ((4 * (size_t)N + 15) & ~(size_t)15));
-    IoLaunch<R>::egest(N, T.cur, A_.rdot, A_.color, A_.F, A_.new_heading, o, stream_);
+    IoLaunch<R>::egest(N, T.cur, A_.F, A_.new_heading, o, stream_);
     launches_++;
     if (r3d) CK(cudaMemcpyAsync(r3d, o.r3d, 24 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
     if (vid) CK(cudaMemcpyAsync(vid, o.vid, 4 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
@@ -795,7 +885,10 @@ template <typename R> int Engine<R>::profile_step(const char** names, double* ms
 {
     CK(cudaSetDevice(device_));
     if (this->N == 0) return 0;
-    static const char* kNames[] = {"count_keys", "scan", "reorder", "neigh_force_align", "wrap_project"};
+    static const char* kEuclid[] = {"step_fused", "scan", "scatter"};
+    static const char* kTable[] = {"neigh_table", "wrap_project", "scan", "scatter"};
+    const char** kNames = P_.neigh_mode == T2D_NEIGH_EUCLID ? kEuclid : kTable;
+    if (!sorted_) resort(false);
     cudaEvent_t ev[8];
     for (auto& e : ev) CK(cudaEventCreate(&e));
     int nev = 0;

@@ -128,13 +128,13 @@ void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s)
 // ---------------------------------------------------------------------------------------------------
 // observables: sum cos n, sum sin n, sum |rdot| over the resident particles
 // ---------------------------------------------------------------------------------------------------
-template <typename R2>
-__global__ void __launch_bounds__(256) k_observables(const int2* __restrict__ hv, const R2* __restrict__ rdot, int N,
+template <typename R>
+__global__ void __launch_bounds__(256) k_observables(const Pos3<R>* __restrict__ pos, const Real2<R>* __restrict__ rdot, int N,
                                                      const double2* __restrict__ trig, double* out)
 {
     double sc = 0, ss = 0, sp = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        int n = hv[i].x;
+        int n = (int)pos[i].w;
         double c, s;
         if (n >= TRIG_MIN && n <= TRIG_MAX) {
             double2 t = trig[n - TRIG_MIN];
@@ -176,16 +176,16 @@ __global__ void __launch_bounds__(256) k_observables(const int2* __restrict__ hv
     }
 }
 
-void launch_observables(const int2* hv, const void* rdot, int is_f32, int N, const double2* trig, double* out8, cudaStream_t s)
+void launch_observables(const void* pos, const void* rdot, int is_f32, int N, const double2* trig, double* out8, cudaStream_t s)
 {
     cudaMemsetAsync(out8, 0, sizeof(double) * T2D_OBS_LEN, s);
     if (N <= 0) return;
     int grid = (N + 255) / 256;
     if (grid > 1184) grid = 1184;   // 148 SMs x 8 resident blocks
     if (is_f32)
-        k_observables<Real2<float>><<<grid, 256, 0, s>>>(hv, (const Real2<float>*)rdot, N, trig, out8);
+        k_observables<float><<<grid, 256, 0, s>>>((const Pos3<float>*)pos, (const Real2<float>*)rdot, N, trig, out8);
     else
-        k_observables<Real2<double>><<<grid, 256, 0, s>>>(hv, (const Real2<double>*)rdot, N, trig, out8);
+        k_observables<double><<<grid, 256, 0, s>>>((const Pos3<double>*)pos, (const Real2<double>*)rdot, N, trig, out8);
 }
 
 }  // namespace t2d

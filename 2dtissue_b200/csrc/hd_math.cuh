@@ -8,15 +8,26 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "cr_tables.h"
+
 #if defined(__CUDACC__)
 #define T2D_HD __host__ __device__ __forceinline__
 #else
 #define T2D_HD inline
 #endif
 
+// products and sums that must round separately even in a translation unit compiled with FMA contraction
+#if defined(__CUDA_ARCH__)
+#define T2D_DMUL(a, b) __dmul_rn((a), (b))
+#define T2D_DADD(a, b) __dadd_rn((a), (b))
+#else
+#define T2D_DMUL(a, b) ((a) * (b))
+#define T2D_DADD(a, b) ((a) + (b))
+#endif
+
 namespace t2d {
 
-constexpr int WRAP_CAP = 64;               // seam re-entry rounds before T2D_FAULT_WRAP_CAP
+constexpr int WRAP_CAP = 4096;            // seam re-entry rounds before T2D_FAULT_WRAP_CAP (the reference loops until inside)
 constexpr int TRIG_MIN = -3600;            // host-built cos/sin table covers integer degrees [TRIG_MIN, TRIG_MAX]
 constexpr int TRIG_MAX = 1079;
 constexpr int TRIG_N = TRIG_MAX - TRIG_MIN + 1;
@@ -219,7 +230,53 @@ T2D_HD double philox_uniform(uint64_t seed, uint64_t step, uint32_t id)
 T2D_HD double noise_deg(double eta360, uint64_t seed, uint64_t step, uint32_t id)
 {
     double u = philox_uniform(seed, step, id);
-    return eta360 * (u - 0.5);
+    return T2D_DMUL(eta360, T2D_DADD(u, -0.5));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Mean angle in degrees exactly as OrientationHelper::mean_unit_circle_vector_angle_degrees produces it
+// (OrientationHelper.cpp:102-116):  a = atan2(my, mx) * RAD_TO_DEG;  if (a < 0) a += 360.
+// The caller truncates a to int, and for aligned or isolated particles the true angle IS an integer degree,
+// so the last ulp of atan2 decides the heading.  glibc's atan2 is correctly rounded on these inputs (checked
+// exhaustively over the tie family in tests/test_hd_math_cpu.py); CUDA's is only 2-ulp.  So atan2 is rebuilt
+// here correctly rounded, without calling atan2 in double at all:
+//     theta = m*pi/180 + eps,  m = nearest integer degree (from a float atan2f),
+//     tan(eps) = (y*C - x*S) / (x*C + y*S)  with C,S = cos/sin(m deg) as double-doubles (cr_tables.h),
+// the numerator evaluated with error-free products (fma) so that eps is good to ~1e-32 absolute, then
+// theta = fl(p_hi + fl(p_lo + eps)).  All later operations are plain IEEE double ops, identical on both sides.
+// `tab` = kCrTable (host) or its device copy.  *tie is set when |a - rint(a)| < 1e-9 (diagnostic counter).
+// ---------------------------------------------------------------------------------------------------
+T2D_HD double mean_angle_degrees_cr(double mx, double my, const CrEntry* tab, bool* tie)
+{
+    double theta;
+    if (mx == 0.0 && my == 0.0) {
+        theta = atan2(my, mx);   // IEEE special cases (+-0, +-pi)
+    } else {
+        const double ay = fabs(my);
+        float af = atan2f((float)ay, (float)mx) * 57.29577951308232f;
+        int m = (int)rintf(af);
+        m = m < 0 ? 0 : (m > 180 ? 180 : m);
+        const CrEntry e = tab[m];
+        const double p1 = T2D_DMUL(ay, e.c_hi), e1 = fma(ay, e.c_hi, -p1);
+        const double p2 = T2D_DMUL(mx, e.s_hi), e2 = fma(mx, e.s_hi, -p2);
+        const double hi = T2D_DADD(p1, -p2);                     // exact (Sterbenz) wherever it matters
+        const double bb = T2D_DADD(hi, -p1);
+        const double er = T2D_DADD(T2D_DADD(p1, -T2D_DADD(hi, -bb)), T2D_DADD(-p2, -bb));   // two-sum remainder elsewhere
+        const double lo = T2D_DADD(T2D_DADD(T2D_DADD(T2D_DADD(e1, -e2), T2D_DMUL(ay, e.c_lo)), -T2D_DMUL(mx, e.s_lo)), er);
+        const double num = T2D_DADD(hi, lo);
+        const double den = T2D_DADD(T2D_DMUL(mx, e.c_hi), T2D_DMUL(ay, e.s_hi));
+        const double tt = num / den;                             // tan(eps), |eps| < 0.01
+        const double t2 = T2D_DMUL(tt, tt);
+        const double ser = T2D_DADD(1.0 / 3.0, -T2D_DMUL(t2, 0.2));
+        const double eps = T2D_DADD(tt, -T2D_DMUL(T2D_DMUL(tt, t2), ser));
+        const double s = T2D_DADD(e.p_lo, eps);
+        theta = T2D_DADD(e.p_hi, s);
+        if (signbit(my)) theta = -theta;
+    }
+    double a = T2D_DMUL(theta, RAD_TO_DEG_D);
+    if (a < 0) a = T2D_DADD(a, 360.0);
+    if (tie) *tie = fabs(a - rint(a)) < 1e-9;
+    return a;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -31,51 +31,50 @@ template <typename R> __global__ void __launch_bounds__(256) k_ingest(int N, Hos
     if (i >= N) return;
     Real2<R> u = {(R)in.uv[i], (R)in.uv[N + i]};
     p.uv[i] = u;
-    int2 hv = {in.heading ? in.heading[i] : 0, in.vid ? in.vid[i] : 0};
-    p.hv[i] = hv;
-    Pos3<R> X = {R(0), R(0), R(0), R(0)};
+    Pos3<R> X = {R(0), R(0), R(0), (R)(in.heading ? in.heading[i] : 0)};
     if (in.r3d) {
         X.x = (R)in.r3d[i];
         X.y = (R)in.r3d[N + i];
         X.z = (R)in.r3d[2 * N + i];
     }
-    p.X[i] = X;
-    p.face[i] = -1;
-    p.id[i] = in.ids ? in.ids[i] : (uint32_t)i;
-    if (p.origin != p.id) p.origin[i] = (uint32_t)i;
+    p.pos[i] = X;
+    p.aux[i] = make_int4(in.vid ? in.vid[i] : 0, -1, (int)(in.ids ? in.ids[i] : (uint32_t)i), i);
+    Real2<R> z = {R(0), R(0)};
+    p.rdot[i] = z;
+    p.color[i] = 0;
 }
 
-// slot s holds the particle that sits at index origin[s] of the caller's arrays
+// slot s holds the particle that sits at index aux[s].w of the caller's arrays
 template <typename R>
-__global__ void __launch_bounds__(256) k_egest(int N, ParticleArrays<R> p, const Real2<R>* rdot, const int* color,
-                                               const Real2<R>* F, const int* new_heading, HostViewOut out)
+__global__ void __launch_bounds__(256) k_egest(int N, ParticleArrays<R> p, const Real2<R>* F, const int* new_heading,
+                                               HostViewOut out)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    const int o = (int)p.origin[s];
+    const int4 ax = p.aux[s];
+    const int o = ax.w;
     if (out.uv) {
         Real2<R> u = p.uv[s];
         out.uv[o] = (double)u.x;
         out.uv[N + o] = (double)u.y;
     }
-    if (out.heading || out.vid) {
-        int2 hv = p.hv[s];
-        if (out.heading) out.heading[o] = hv.x;
-        if (out.vid) out.vid[o] = hv.y;
-    }
-    if (out.r3d) {
-        Pos3<R> X = p.X[s];
-        out.r3d[o] = (double)X.x;
-        out.r3d[N + o] = (double)X.y;
-        out.r3d[2 * N + o] = (double)X.z;
+    if (out.vid) out.vid[o] = ax.x;
+    if (out.face) out.face[o] = ax.y;
+    if (out.r3d || out.heading) {
+        Pos3<R> X = p.pos[s];
+        if (out.heading) out.heading[o] = (int)X.w;
+        if (out.r3d) {
+            out.r3d[o] = (double)X.x;
+            out.r3d[N + o] = (double)X.y;
+            out.r3d[2 * N + o] = (double)X.z;
+        }
     }
     if (out.rdot) {
-        Real2<R> r = rdot[s];
+        Real2<R> r = p.rdot[s];
         out.rdot[o] = (double)r.x;
         out.rdot[N + o] = (double)r.y;
     }
-    if (out.color) out.color[o] = color[s];
-    if (out.face) out.face[o] = p.face[s];
+    if (out.color) out.color[o] = p.color[s];
     if (out.F) {
         Real2<R> f = F[s];
         out.F[o] = (double)f.x;
@@ -108,8 +107,8 @@ template <typename R> __global__ void __launch_bounds__(256) k_outN(int N, int c
 
 template <typename R> struct IoLaunch {
     static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s);
-    static void egest(int N, const ParticleArrays<R>& p, const Real2<R>* rdot, const int* color, const Real2<R>* F,
-                      const int* new_heading, const HostViewOut& out, cudaStream_t s);
+    static void egest(int N, const ParticleArrays<R>& p, const Real2<R>* F, const int* new_heading, const HostViewOut& out,
+                      cudaStream_t s);
     static void in2(int N, const double* src, Real2<R>* dst, cudaStream_t s);
     static void out2(int N, const Real2<R>* src, double* dst, cudaStream_t s);
     static void outN(int N, int cols, const R* src, double* dst, cudaStream_t s);
@@ -121,10 +120,10 @@ template <typename R> void IoLaunch<R>::ingest(int N, const HostViewIn& in, cons
     if (N > 0) k_ingest<R><<<(N + 255) / 256, 256, 0, s>>>(N, in, p);
 }
 template <typename R>
-void IoLaunch<R>::egest(int N, const ParticleArrays<R>& p, const Real2<R>* rdot, const int* color, const Real2<R>* F,
-                        const int* new_heading, const HostViewOut& out, cudaStream_t s)
+void IoLaunch<R>::egest(int N, const ParticleArrays<R>& p, const Real2<R>* F, const int* new_heading, const HostViewOut& out,
+                        cudaStream_t s)
 {
-    if (N > 0) k_egest<R><<<(N + 255) / 256, 256, 0, s>>>(N, p, rdot, color, F, new_heading, out);
+    if (N > 0) k_egest<R><<<(N + 255) / 256, 256, 0, s>>>(N, p, F, new_heading, out);
 }
 template <typename R> void IoLaunch<R>::in2(int N, const double* src, Real2<R>* dst, cudaStream_t s)
 {

@@ -1,11 +1,13 @@
 // kernels.cuh — the step's CUDA kernels, templated on the arithmetic type.
 //
-//   k_count_keys      bucket key per particle (nearest-vertex id | hashed 3-D cell) + arrival rank (K1)
-//   k_reorder         counting-sort scatter of the SoA state into bucket order (K2)
-//   k_neigh_table     stage 2-5 for the vertex-distance-table criterion: one CTA per bucket, neighbour
+//   k_bin             bucket key of every resident particle + arrival rank + histogram (K1; after uploads only —
+//                     during stepping the producing kernel emits the next keys itself)
+//   k_scatter         counting-sort scatter of the SoA state into bucket order (K2)
+//   k_step_euclid     stages 2-5 FUSED for the Euclidean criterion: sparse-voxel cell list, 2x2x2 octant
+//                     stencil, force + alignment (+ noise), Euler, seam re-entry, re-projection, next key (K3-K5)
+//   k_neigh_table     stages 2-4a for the vertex-distance-table criterion: one CTA per bucket, neighbour
 //                     buckets from the thresholded CSR row, shared-memory staging, exact ascending-id sums (K3)
-//   k_neigh_euclid    stage 2-5 for the Euclidean criterion: hashed cell list, 2x2x2 octant stencil (K3)
-//   k_wrap_project    seam re-entry + UV point location + 3-D lift + validation flags (K4+K5)
+//   k_wrap_project    table mode: seam re-entry + UV point location + 3-D lift + validation + next key (K4+K5)
 //
 // No tensor cores anywhere: the work is gather/scatter + O(10^2) flop per particle.
 #pragma once
@@ -16,55 +18,24 @@ namespace t2d {
 // ---------------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------------
-template <typename R> struct TrigLookup;
-template <> struct TrigLookup<double> {
-    static __device__ __forceinline__ void get(const StepArgs<double>& a, int n, double& c, double& s, unsigned& fb)
-    {
-        if (n >= TRIG_MIN && n <= TRIG_MAX) {
-            double2 t = __ldg(&a.trig_d[n - TRIG_MIN]);
-            c = t.x;
-            s = t.y;
-        } else {   // outside the host-built table: CUDA libm (may differ from glibc in the last ulp) — counted
-            double r = (double)n * DEG_TO_RAD_D;
-            c = cos(r);
-            s = sin(r);
-            fb++;
-        }
-    }
-};
-template <> struct TrigLookup<float> {
-    static __device__ __forceinline__ void get(const StepArgs<float>& a, int n, float& c, float& s, unsigned& fb)
-    {
-        if (n >= TRIG_MIN && n <= TRIG_MAX) {
-            float2 t = __ldg(&a.trig_f[n - TRIG_MIN]);
-            c = t.x;
-            s = t.y;
-        } else {
-            double r = (double)n * DEG_TO_RAD_D;
-            c = (float)cos(r);
-            s = (float)sin(r);
-            fb++;
-        }
-    }
-};
-
-__device__ __forceinline__ uint32_t cell_hash(int cx, int cy, int cz, uint32_t mask)
+// (cos, sin) of an integer-degree heading exactly as the reference's libm call sees it (host-built table)
+__device__ __forceinline__ double2 trig_lookup(const double2* __restrict__ tab, int n, unsigned long long& fb)
 {
-    uint32_t h = (uint32_t)cx * 73856093u ^ (uint32_t)cy * 19349663u ^ (uint32_t)cz * 83492791u;
-    h ^= h >> 15;
-    h *= 0x2c1b3c6du;
-    h ^= h >> 12;
-    return h & mask;
+    if (n >= TRIG_MIN && n <= TRIG_MAX) return __ldg(&tab[n - TRIG_MIN]);
+    // outside the host-built table: CUDA libm (may differ from glibc in the last ulp) — counted
+    double r = (double)n * DEG_TO_RAD_D;
+    fb++;
+    return make_double2(cos(r), sin(r));
 }
 
 template <typename R> __device__ __forceinline__ R dev_floor(R v);
 template <> __device__ __forceinline__ double dev_floor<double>(double v) { return floor(v); }
 template <> __device__ __forceinline__ float dev_floor<float>(float v) { return floorf(v); }
 
-// block-wide accumulation of diagnostic counters: one global atomic per block per counter
+// block-wide accumulation of diagnostic counters: one global atomic per warp per non-zero counter
 struct BlockCounters {
     unsigned long long pairs = 0, ties_cut = 0, ties_trunc = 0, wraps = 0, caps = 0, order_fb = 0, trig_fb = 0,
-                       loc_fb = 0, max_row = 0, lost = 0, nonfinite = 0;
+                       loc_fb = 0, max_row = 0, lost = 0, nonfinite = 0, cell_fb = 0;
     unsigned fault = 0;
 };
 
@@ -82,34 +53,40 @@ __device__ __forceinline__ unsigned long long warp_max(unsigned long long v)
     return v;
 }
 
-// every thread of the block must call this (once, at the end of the kernel)
+// every thread of the block must call this (once, at the end of the kernel); only counters that some lane of
+// the warp touched are reduced, so the common case costs a handful of votes
 __device__ __forceinline__ void flush_counters(const BlockCounters& c, DevCounters* g)
 {
-    unsigned f = c.fault;
-    for (int o = 16; o > 0; o >>= 1) f |= __shfl_down_sync(0xffffffffu, f, o);
-    unsigned long long v[10] = {c.pairs, c.ties_cut, c.ties_trunc, c.wraps, c.caps,
-                                c.order_fb, c.trig_fb, c.loc_fb, c.lost, c.nonfinite};
+    const unsigned long long v[11] = {c.pairs, c.ties_cut, c.ties_trunc, c.wraps, c.caps, c.order_fb,
+                                      c.trig_fb, c.loc_fb, c.lost, c.nonfinite, c.cell_fb};
+    unsigned long long* const dst[11] = {&g->pairs_in_range, &g->ties_cutoff, &g->ties_trunc, &g->wraps, &g->wrap_cap_hits,
+                                         &g->order_fallbacks, &g->trig_fallbacks, &g->locate_fallbacks, &g->lost, &g->nonfinite,
+                                         &g->cell_fallbacks};
+    const bool lane0 = (threadIdx.x & 31) == 0;
 #pragma unroll
-    for (int q = 0; q < 10; ++q) v[q] = warp_sum(v[q]);
-    unsigned long long mr = warp_max(c.max_row);
-    if ((threadIdx.x & 31) == 0) {
-        unsigned long long* dst[10] = {&g->pairs_in_range, &g->ties_cutoff, &g->ties_trunc, &g->wraps, &g->wrap_cap_hits,
-                                       &g->order_fallbacks, &g->trig_fallbacks, &g->locate_fallbacks, &g->lost, &g->nonfinite};
-#pragma unroll
-        for (int q = 0; q < 10; ++q)
-            if (v[q]) atomicAdd(dst[q], v[q]);
-        if (mr) atomicMax(&g->max_row, mr);
-        if (f) atomicOr(&g->fault, f);
+    for (int q = 0; q < 11; ++q) {
+        if (__any_sync(0xffffffffu, v[q] != 0)) {
+            unsigned long long t = warp_sum(v[q]);
+            if (lane0) atomicAdd(dst[q], t);
+        }
+    }
+    if (__any_sync(0xffffffffu, c.max_row != 0)) {
+        unsigned long long mr = warp_max(c.max_row);
+        if (lane0) atomicMax(&g->max_row, mr);
+    }
+    if (__any_sync(0xffffffffu, c.fault != 0)) {
+        unsigned f = c.fault;
+        for (int o = 16; o > 0; o >>= 1) f |= __shfl_down_sync(0xffffffffu, f, o);
+        if (lane0) atomicOr(&g->fault, f);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1: bucket key + arrival rank
+// sparse voxel index: 3-D cell -> compact bucket id
 // ---------------------------------------------------------------------------------------------------
-template <typename R> __device__ __forceinline__ void cell_coords(const StepArgs<R>& a, const Pos3<R>& X, int c[3], int side[3])
+template <typename R> __device__ __forceinline__ void cell_coords(const DevVox<R>& vx, const Pos3<R>& X, int c[3], int side[3])
 {
-    R q[3] = {(X.x - a.mesh.eucl_origin[0]) * a.inv_cell, (X.y - a.mesh.eucl_origin[1]) * a.inv_cell,
-              (X.z - a.mesh.eucl_origin[2]) * a.inv_cell};
+    R q[3] = {(X.x - vx.origin[0]) * vx.inv_cell, (X.y - vx.origin[1]) * vx.inv_cell, (X.z - vx.origin[2]) * vx.inv_cell};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         R fl = dev_floor<R>(q[k]);
@@ -118,165 +95,398 @@ template <typename R> __device__ __forceinline__ void cell_coords(const StepArgs
     }
 }
 
-template <typename R> __global__ void __launch_bounds__(256) k_count_keys(StepArgs<R> a)
+template <typename R> __device__ __forceinline__ int vox_index(const DevVox<R>& vx, int cx, int cy, int cz)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.N) return;
-    uint32_t key;
-    if (a.mode == T2D_NEIGH_TABLE) {
-        key = (uint32_t)a.cur.hv[i].y;
-    } else {
-        int c[3], side[3];
-        cell_coords<R>(a, a.cur.X[i], c, side);
-        key = cell_hash(c[0], c[1], c[2], a.hash_mask);
+    if ((unsigned)cx >= (unsigned)vx.ncx || (unsigned)cy >= (unsigned)vx.ncy || (unsigned)cz >= (unsigned)vx.ncz) return -1;
+    const int b = ((cz >> 2) * vx.nby + (cy >> 2)) * vx.nbx + (cx >> 2);
+    const uint4 e = __ldg(&vx.blocks[b]);
+    const unsigned bit = ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3);
+    const unsigned long long bm = ((unsigned long long)e.y << 32) | e.x;
+    if (!((bm >> bit) & 1ull)) return -1;
+    return (int)e.z + __popcll(bm & ((1ull << bit) - 1ull));
+}
+
+// bucket key of a particle: nearest-vertex id (table criterion) or compact 3-D cell (Euclidean criterion)
+template <typename R> __device__ __forceinline__ uint32_t bucket_key(const StepArgs<R>& a, const Pos3<R>& X, int vid, BlockCounters& bc)
+{
+    if (a.mode == T2D_NEIGH_TABLE) return (uint32_t)vid;
+    int c[3], side[3];
+    cell_coords<R>(a.vox, X, c, side);
+    int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
+    if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket, searched by everyone
+        bc.cell_fb++;
+        idx = a.vox.M;
     }
-    a.key[i] = key;
-    a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+    return (uint32_t)idx;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2: scatter into bucket order
+// setup: voxelise the mesh surface into the sparse cell index.  One warp per face; lanes stride over the
+// cells of the face's (grown) bounding box and mark those whose centre is within `reach` of the triangle
+// (reach = half a cell diagonal + tolerance, so every cell the triangle touches is marked).
+// occ: one 64-bit occupancy word per 4x4x4 block.
 // ---------------------------------------------------------------------------------------------------
-template <typename R> __global__ void __launch_bounds__(256) k_reorder(StepArgs<R> a)
+__device__ __forceinline__ double point_triangle_dist2_3d(const double p[3], const double a[3], const double b[3], const double c[3])
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.N) return;
-    int s = a.start[a.key[i]] + (int)a.rank[i];
-    a.alt.uv[s] = a.cur.uv[i];
-    a.alt.hv[s] = a.cur.hv[i];
-    a.alt.X[s] = a.cur.X[i];
-    a.alt.face[s] = a.cur.face[i];
-    a.alt.id[s] = a.cur.id[i];
-    if (a.cur.origin != a.cur.id) a.alt.origin[s] = a.cur.origin[i];
+    double ab[3], ac[3], ap[3];
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+    auto dot = [](const double* u, const double* v) { return u[0] * v[0] + u[1] * v[1] + u[2] * v[2]; };
+    auto d2to = [&](double v, double w) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) { double e = a[k] + ab[k] * v + ac[k] * w - p[k]; s += e * e; }
+        return s;
+    };
+    double d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) return d2to(0, 0);
+    double bp[3] = {p[0] - b[0], p[1] - b[1], p[2] - b[2]};
+    double d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= 0 && d4 <= d3) return d2to(1, 0);
+    double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) return d2to(d1 / (d1 - d3), 0);
+    double cp[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+    double d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) return d2to(0, 1);
+    double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) return d2to(0, d2 / (d2 - d6));
+    double va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        return d2to(1 - w, w);
+    }
+    double den = 1.0 / (va + vb + vc);
+    return d2to(vb * den, vc * den);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// shared tail of K3: speed, Euler step, new heading.
-//   Locomotion::simulate_flight lines 71-84 (Locomotion.cpp) + OrientationHelper.cpp:67-70 (+ noise)
-// ---------------------------------------------------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ void finish_particle(const StepArgs<R>& a, int slot, Real2<R> ui, int heading, uint32_t id, R fx,
-                                                R fy, R mx, R my, int color, BlockCounters& bc)
+__global__ void __launch_bounds__(256) k_voxelize(DevMesh<R> m, double ox, double oy, double oz, double cs, double reach,
+                                                  int ncx, int ncy, int ncz, int nbx, int nby, unsigned long long* occ)
 {
-    R absF = rsqrt_exact<R>(fx * fx + fy * fy);   // F_track.rowwise().norm()
-    R c, s;
-    unsigned tf = 0;
-    TrigLookup<R>::get(a, heading, c, s, tf);     // angles_to_unit_vectors(n) with the OLD heading
-    bc.trig_fb += tf;
-    absF = absF + a.v0;
-    R rx = c * absF, ry = s * absF;
-    Real2<R> rd = {rx, ry};
-    a.rdot[slot] = rd;
-    Real2<R> un = {ui.x + rx * a.step_size, ui.y + ry * a.step_size};
-    a.uv_new[slot] = un;
-    if (a.write_F) {
-        Real2<R> Fv = {fx, fy};
-        a.F[slot] = Fv;
-    }
-    a.color[slot] = color;
-
-    // mean_unit_circle_vector_angle_degrees, OrientationHelper.cpp:84-116 (Eigen normalize(): z>0 guard)
-    double angle_degrees;
-    if (sizeof(R) == 8) {
-        double dmx = (double)mx, dmy = (double)my;
-        double z = dmx * dmx + dmy * dmy;
-        if (z > 0.0) {
-            double sq = sqrt(z);
-            dmx = dmx / sq;
-            dmy = dmy / sq;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < m.F; f += warps) {
+        const int4 tv = m.tri_vid[f];
+        const Pos3<R> A = m.x3d[tv.x], B = m.x3d[tv.y], C = m.x3d[tv.z];
+        const double a[3] = {(double)A.x, (double)A.y, (double)A.z}, b[3] = {(double)B.x, (double)B.y, (double)B.z},
+                     c[3] = {(double)C.x, (double)C.y, (double)C.z};
+        const double org[3] = {ox, oy, oz};
+        const int nc[3] = {ncx, ncy, ncz};
+        int lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+            double mn = fmin(a[k], fmin(b[k], c[k])) - reach, mx = fmax(a[k], fmax(b[k], c[k])) + reach;
+            lo[k] = max(0, (int)floor((mn - org[k]) / cs));
+            hi[k] = min(nc[k] - 1, (int)floor((mx - org[k]) / cs));
         }
-        angle_degrees = atan2(dmy, dmx) * RAD_TO_DEG_D;
-        if (angle_degrees < 0) angle_degrees += 360.0;
-        if (fabs(angle_degrees - rint(angle_degrees)) < 1e-9) bc.ties_trunc++;
-    } else {
-        angle_degrees = (double)atan2f((float)my, (float)mx) * RAD_TO_DEG_D;
-        if (angle_degrees < 0) angle_degrees += 360.0;
-    }
-    int avg = (int)angle_degrees;
-    if (a.eta360 != 0.0) avg = (int)((double)avg + noise_deg(a.eta360, a.seed, a.step, id));
-    a.new_heading[slot] = avg;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K3 (Euclidean criterion).  d_ij = ||X_i - X_j|| on the 3-D positions of the previous projection.
-// Hashed cell list with cell edge 2*rmax: a neighbour within rmax lies in the particle's own cell or the
-// adjacent one on the nearer side per axis -> 8 buckets.  EXACT: in-range neighbours are gathered, sorted by
-// global id and summed in that order (the reference sums in ascending j), so forces and headings are
-// bit-identical; rows longer than KMAX fall back to unordered sums (counted).
-// ---------------------------------------------------------------------------------------------------
-constexpr int EUCLID_KMAX = 48;
-
-template <typename R, bool COLLECT>
-__device__ __forceinline__ void euclid_visit(const StepArgs<R>& a, int i, const Pos3<R>& Xi, const Real2<R>& ui,
-                                             const uint32_t keys[8], R& fx, R& fy, R& mx, R& my, int& color,
-                                             unsigned long long* list, int& cnt, bool& overflow, BlockCounters& bc)
-{
-    const R rmax = a.two_sigma > a.color_r ? a.two_sigma : a.color_r;
-    const R rmax2 = rmax * rmax * R(1.0001);
-#pragma unroll 1
-    for (int m = 0; m < 8; ++m) {
-        bool dup = false;
-        for (int p = 0; p < m; ++p) dup |= (keys[p] == keys[m]);
-        if (dup) continue;
-        int s = a.start[keys[m]], e = a.start[keys[m] + 1];
-        for (int j = s; j < e; ++j) {
-            Pos3<R> Xj = a.cur.X[j];
-            R dx = Xi.x - Xj.x, dy = Xi.y - Xj.y, dz = Xi.z - Xj.z;
-            R d2 = dx * dx + dy * dy + dz * dz;
-            if (d2 > rmax2) continue;
-            R d = (j == i) ? R(0) : rsqrt_exact<R>(d2);
-            if (COLLECT) {   // first pass: colour + tie statistics are order independent
-                if (d != R(0) && d <= a.color_r) color++;
-                if (d == a.two_sigma) bc.ties_cut++;
-            }
-            if (!(d < a.two_sigma)) continue;
-            if (COLLECT) {
-                if (cnt < EUCLID_KMAX)
-                    list[cnt++] = ((unsigned long long)a.cur.id[j] << 32) | (unsigned)j;
-                else
-                    overflow = true;
-            } else {
-                R c, sn;
-                unsigned tf = 0;
-                TrigLookup<R>::get(a, a.cur.hv[j].x, c, sn, tf);
-                bc.trig_fb += tf;
-                mx += c;
-                my += sn;
-                if (j != i) {
-                    bc.pairs++;
-                    R dd = d;
-                    if (dd == R(0)) dd += R(0.001);
-                    R Fij = pair_fij<R>(a.k, a.two_sigma, dd);
-                    Real2<R> uj = a.cur.uv[j];
-                    fx += Fij * ((ui.x - uj.x) / dd);
-                    fy += Fij * ((ui.y - uj.y) / dd);
-                }
+        const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
+        if (ex <= 0 || ey <= 0 || ez <= 0) continue;
+        const long long total = (long long)ex * ey * ez;
+        for (long long q = lane; q < total; q += 32) {
+            const int cx = lo[0] + (int)(q % ex), cy = lo[1] + (int)((q / ex) % ey), cz = lo[2] + (int)(q / ((long long)ex * ey));
+            const double p[3] = {ox + (cx + 0.5) * cs, oy + (cy + 0.5) * cs, oz + (cz + 0.5) * cs};
+            if (point_triangle_dist2_3d(p, a, b, c) <= reach * reach) {
+                const size_t blk = ((size_t)(cz >> 2) * nby + (cy >> 2)) * nbx + (cx >> 2);
+                const unsigned bit = ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3);
+                atomicOr(&occ[blk], 1ull << bit);
             }
         }
     }
 }
 
-template <typename R, bool EXACT> __global__ void __launch_bounds__(128) k_neigh_euclid(StepArgs<R> a)
+// ---------------------------------------------------------------------------------------------------
+// K1: bucket key + arrival rank + histogram of the resident state (after uploads)
+// ---------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(256) k_bin(StepArgs<R> a)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     BlockCounters bc;
     if (i < a.N) {
-        Pos3<R> Xi = a.cur.X[i];
-        Real2<R> ui = a.cur.uv[i];
-        int2 hvi = a.cur.hv[i];
-        int c[3], side[3];
-        cell_coords<R>(a, Xi, c, side);
-        uint32_t keys[8];
+        uint32_t key = bucket_key<R>(a, a.cur.pos[i], a.cur.aux[i].x, bc);
+        a.key[i] = key;
+        a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+    }
+    flush_counters(bc, a.counters);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: scatter cur -> alt in bucket order
+// ---------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<R> a)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const int s = a.start[a.key[i]] + (int)a.rank[i];
+    a.alt.pos[s] = a.cur.pos[i];
+    a.alt.uv[s] = a.cur.uv[i];
+    a.alt.aux[s] = a.cur.aux[i];
+    a.alt.rdot[s] = a.cur.rdot[i];
+    a.alt.color[s] = a.cur.color[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// heading after alignment: OrientationHelper::calculate_average_n_within_distance lines 62-70 +
+// mean_unit_circle_vector_angle_degrees (OrientationHelper.cpp:84-116).  mx,my = sum of the neighbours'
+// unit vectors in double on BOTH precision paths, so that the integer heading of the fp32 fast path equals
+// the fp64 one whenever the neighbour sets agree (the truncation to int makes the last ulp matter).
+// ---------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ int heading_from_sum(const StepArgs<R>& a, double mx, double my, uint32_t id, BlockCounters& bc)
+{
+    double z = T2D_DADD(T2D_DMUL(mx, mx), T2D_DMUL(my, my));   // Eigen normalize(): z = squaredNorm(); if (z > 0) v /= sqrt(z)
+    if (z > 0.0) {
+        double sq = sqrt(z);
+        mx = mx / sq;
+        my = my / sq;
+    }
+    bool tie;
+    double angle_degrees = mean_angle_degrees_cr(mx, my, a.cr, &tie);
+    if (tie) bc.ties_trunc++;
+    int avg = (int)angle_degrees;
+    if (a.eta360 != 0.0) avg = (int)T2D_DADD((double)avg, noise_deg(a.eta360, a.seed, a.step, id));
+    return avg;
+}
+
+// speed and velocity: Locomotion::simulate_flight lines 71-81 (Locomotion.cpp)
+template <typename R>
+__device__ __forceinline__ Real2<R> velocity_from_force(const StepArgs<R>& a, int heading, R fx, R fy, BlockCounters& bc)
+{
+    R absF = rsqrt_exact<R>(fx * fx + fy * fy);   // F_track.rowwise().norm()
+    double2 t = trig_lookup(a.trig_d, heading, bc.trig_fb);   // angles_to_unit_vectors(n) with the OLD heading
+    absF = absF + a.v0;
+    Real2<R> rd = {(R)t.x * absF, (R)t.y * absF};
+    return rd;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5 core: UV point location + lift.  The reference takes the arg-min of (2-D point-triangle distance,
+// face index) over ALL faces (CellHelper.cpp:106-117).  The containing face has distance ~1e-17, so the
+// arg-min lies among the faces whose (slightly grown) bounding box covers the point: the uniform grid
+// cell lists exactly those, in ascending face id; the same distance function decides between them.
+// ---------------------------------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ int locate_face(const DevMesh<R>& m, R px, R py, BlockCounters& bc)
+{
+    const int G = m.G;
+    int gi = (int)dev_floor<R>(px * (R)G), gj = (int)dev_floor<R>(py * (R)G);
+    gi = gi < 0 ? 0 : (gi > G - 1 ? G - 1 : gi);
+    gj = gj < 0 ? 0 : (gj > G - 1 ? G - 1 : gj);
+    const int cell = gj * G + gi;
+    int best = -1;
+    R bd = 0;
+    const int qs = m.gstart[cell], qe = m.gstart[cell + 1];
+    for (int q = qs; q < qe; ++q) {
+        int f = m.gfaces[q];
+        TriUV<R> t = m.tri[f];
+        R d = point_triangle_distance<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
+        if (best < 0 || d < bd) {
+            bd = d;
+            best = f;
+        }
+        if (bd == R(0)) break;   // ascending face id: nothing later can beat (0, f)
+    }
+    const R cover_eps = (sizeof(R) == 8) ? R(1e-9) : R(1e-5);
+    if (best < 0 || !(bd <= cover_eps)) {   // not covered by the cell list (or NaN): scan all faces like the reference
+        bc.loc_fb++;
+        best = 0;
+        TriUV<R> t0 = m.tri[0];
+        bd = point_triangle_distance<R>(px, py, t0.ax, t0.ay, t0.bx, t0.by, t0.cx, t0.cy);
+        for (int f = 1; f < m.F; ++f) {
+            TriUV<R> t = m.tri[f];
+            R d = point_triangle_distance<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
+            if (d < bd) {
+                bd = d;
+                best = f;
+            }
+        }
+    }
+    return best;
+}
+
+// fp32 fast path only: the face of the previous step still contains the point with a barycentric margin far
+// above fp32 noise -> it is the arg-min (every other face is at least that far away); skip the grid scan.
+__device__ __forceinline__ bool hint_contains(const TriUV<float>& t, float px, float py)
+{
+    const float d = (t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax);
+    const float la = ((t.bx - px) * (t.cy - py) - (t.by - py) * (t.cx - px)) / d;
+    const float lb = ((t.cx - px) * (t.ay - py) - (t.cy - py) * (t.ax - px)) / d;
+    const float lc = 1.0f - la - lb;
+    const float m = 1e-3f;
+    return la >= m && lb >= m && lc >= m;
+}
+
+template <typename R>
+__device__ __forceinline__ void project_point(const DevMesh<R>& m, R px, R py, int hint, int& face, int& vid, Pos3<R>& X,
+                                              BlockCounters& bc)
+{
+    int f = -1;
+    TriUV<R> t;
+    if constexpr (sizeof(R) == 4) {
+        if (hint >= 0) {
+            t = m.tri[hint];
+            if (hint_contains(t, px, py)) f = hint;
+        }
+    }
+    if (f < 0) {
+        f = locate_face<R>(m, px, py, bc);
+        t = m.tri[f];
+    }
+    int4 tv = m.tri_vid[f];
+    Pos3<R> A = m.x3d[tv.x], B = m.x3d[tv.y], C = m.x3d[tv.z];
+    R Av[3] = {A.x, A.y, A.z}, Bv[3] = {B.x, B.y, B.z}, Cv[3] = {C.x, C.y, C.z}, Xv[3];
+    int which = lift_to_3d<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv);
+    face = f;
+    vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
+    X.x = Xv[0];
+    X.y = Xv[1];
+    X.z = Xv[2];
+}
+
+template <typename R> __device__ __forceinline__ bool dev_finite(R v) { return isfinite(v); }
+
+// stages 4b-5 for one particle: seam re-entry, validation flags, projection.  in/out p, n; out face, vid, X
+template <typename R>
+__device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> old, Real2<R>& p, int& n, int hint, int& face,
+                                                 int& vid, Pos3<R>& X, BlockCounters& bc)
+{
+    int wraps = 0;
+    bool cap = seam_reentry<R>(old.x, old.y, p.x, p.y, n, wraps);
+    bc.wraps += wraps;
+    if (cap) {
+        bc.caps++;
+        bc.fault |= T2D_FAULT_WRAP_CAP;
+    }
+    if (!inside_square<R>(p.x, p.y)) {   // Validation::error_lost_particles
+        bc.lost++;
+        bc.fault |= T2D_FAULT_LOST;
+    }
+    if (!dev_finite<R>(p.x) || !dev_finite<R>(p.y)) {   // Validation::error_invalid_values
+        bc.nonfinite++;
+        bc.fault |= T2D_FAULT_NONFINITE;
+    }
+    project_point<R>(a.mesh, p.x, p.y, wraps == 0 ? hint : -1, face, vid, X, bc);
+    X.w = (R)n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3-K5 fused (Euclidean criterion).  d_ij = ||X_i - X_j|| on the 3-D positions of the previous projection.
+// Cell edge = 2*rmax: a neighbour within rmax lies in the particle's own cell or the adjacent one on the
+// nearer side per axis -> 8 cells, whose particle ranges are contiguous in the sorted state; the 8 ranges
+// (+ the overflow bucket) are walked as ONE flat candidate loop so that lanes do not idle on short cells.
+// EXACT (fp64 parity path): the in-range neighbours are gathered, sorted by global id and summed in that
+// order (the reference sums in ascending j), so forces are bit-identical; rows longer than KMAX fall back
+// to unordered sums (counted).  The fast path sums in visiting order.
+// One thread per particle; the new state goes to `alt` (other particles still read `cur`), together with
+// the particle's next bucket key, arrival rank and the histogram for the counting sort that follows.
+// ---------------------------------------------------------------------------------------------------
+constexpr int EUCLID_KMAX = 48;
+constexpr int STEP_THREADS = 128;
+constexpr int NRANGE = 9;
+
+template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__(STEP_THREADS) k_step_euclid(StepArgs<R> a)
+{
+    __shared__ int s_beg[NRANGE][STEP_THREADS];
+    __shared__ int s_end[NRANGE][STEP_THREADS];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * STEP_THREADS + tid;
+    BlockCounters bc;
+    if (i < a.N) {
+        const Pos3<R> Pi = a.cur.pos[i];
+        const Real2<R> ui = a.cur.uv[i];
+        const int4 ai = a.cur.aux[i];
+        const int heading = (int)Pi.w;
+        {
+            int c[3], side[3];
+            cell_coords<R>(a.vox, Pi, c, side);
 #pragma unroll
-        for (int m = 0; m < 8; ++m)
-            keys[m] = cell_hash(c[0] + ((m & 1) ? side[0] : 0), c[1] + ((m & 2) ? side[1] : 0),
-                                c[2] + ((m & 4) ? side[2] : 0), a.hash_mask);
-        R fx = 0, fy = 0, mx = 0, my = 0;
-        int color = 0, cnt = 0;
-        bool overflow = false;
-        if (EXACT) {
+            for (int m = 0; m < 8; ++m) {
+                int idx = vox_index<R>(a.vox, c[0] + ((m & 1) ? side[0] : 0), c[1] + ((m & 2) ? side[1] : 0),
+                                       c[2] + ((m & 4) ? side[2] : 0));
+                int s = 0, e = 0;
+                if (idx >= 0) {
+                    s = a.start[idx];
+                    e = a.start[idx + 1];
+                }
+                s_beg[m][tid] = s;
+                s_end[m][tid] = e;
+            }
+            s_beg[8][tid] = a.start[a.vox.M];
+            s_end[8][tid] = a.start[a.vox.M + 1];
+        }
+        const R rmax = a.two_sigma > a.color_r ? a.two_sigma : a.color_r;
+        const R rmax2 = rmax * rmax * R(1.0001);
+        R fx = 0, fy = 0;
+        double mx = 0, my = 0;
+        int color = 0;
+        int npairs = 0;
+
+        if constexpr (!EXACT) {
+            // fast path: predicates on squared distances, one rsqrt per in-range pair, sums in visiting order
+            const float r2s = a.two_sigma * a.two_sigma, r2c = a.color_r * a.color_r;
+            const float inv2s = 1.0f / a.two_sigma;
+            int m = 0, j = s_beg[0][tid], e = s_end[0][tid];
+            for (;;) {
+                while (j >= e && m < NRANGE - 1) {
+                    ++m;
+                    j = s_beg[m][tid];
+                    e = s_end[m][tid];
+                }
+                if (j >= e) break;
+                const Pos3<R> Pj = a.cur.pos[j];
+                const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 <= rmax2) {
+                    const bool other = (j != i);
+                    color += (other && d2 > 0.0f && d2 <= r2c) ? 1 : 0;   // _2DTissue::count_particle_neighbors
+                    if (d2 < r2s) {
+                        const double2 t = trig_lookup(a.trig_d, (int)Pj.w, bc.trig_fb);
+                        mx += t.x;
+                        my += t.y;
+                        if (other) {
+                            npairs++;
+                            float rinv = rsqrtf(d2), d = d2 * rinv;
+                            if (d2 == 0.0f) {   // coincident particles: d := 0.001 (ForceHelper.cpp:59-62)
+                                d = 0.001f;
+                                rinv = 1000.0f;
+                            }
+                            const float g = -a.k * (a.two_sigma - d) * inv2s * rinv;   // F_ij / d
+                            const Real2<R> uj = a.cur.uv[j];
+                            fx += g * (ui.x - uj.x);
+                            fy += g * (ui.y - uj.y);
+                        }
+                    }
+                }
+                ++j;
+            }
+        }
+
+        if constexpr (EXACT) {
             unsigned long long list[EUCLID_KMAX];
-            euclid_visit<R, true>(a, i, Xi, ui, keys, fx, fy, mx, my, color, list, cnt, overflow, bc);
+            int cnt = 0;
+            bool overflow = false;
+            // pass 1: every candidate once: colour, cutoff ties, list of in-range neighbours
+            {
+                int m = 0, j = s_beg[0][tid], e = s_end[0][tid];
+                for (;;) {
+                    while (j >= e && m < NRANGE - 1) {
+                        ++m;
+                        j = s_beg[m][tid];
+                        e = s_end[m][tid];
+                    }
+                    if (j >= e) break;
+                    const Pos3<R> Pj = a.cur.pos[j];
+                    const R dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                    const R d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 <= rmax2) {
+                        const R d = (j == i) ? R(0) : rsqrt_exact<R>(d2);
+                        if (d != R(0) && d <= a.color_r) color++;   // _2DTissue::count_particle_neighbors
+                        if (d == a.two_sigma) bc.ties_cut++;
+                        if (d < a.two_sigma) {
+                            if (cnt < EUCLID_KMAX) list[cnt] = ((unsigned long long)(uint32_t)a.cur.aux[j].z << 32) | (unsigned)j;
+                            cnt++;
+                        }
+                    }
+                    ++j;
+                }
+            }
+            overflow = cnt > EUCLID_KMAX;
+            if ((unsigned long long)cnt > bc.max_row) bc.max_row = cnt;
             if (!overflow) {
                 for (int p = 1; p < cnt; ++p) {   // insertion sort by (id, slot)
                     unsigned long long kx = list[p];
@@ -287,69 +497,82 @@ template <typename R, bool EXACT> __global__ void __launch_bounds__(128) k_neigh
                     }
                     list[q + 1] = kx;
                 }
-                for (int p = 0; p < cnt; ++p) {
-                    int j = (int)(unsigned)list[p];
-                    R cj, sj;
-                    unsigned tf = 0;
-                    TrigLookup<R>::get(a, a.cur.hv[j].x, cj, sj, tf);
-                    bc.trig_fb += tf;
-                    mx += cj;
-                    my += sj;
-                    if (j != i) {
-                        bc.pairs++;
-                        Pos3<R> Xj = a.cur.X[j];
-                        R dx = Xi.x - Xj.x, dy = Xi.y - Xj.y, dz = Xi.z - Xj.z;
-                        R dd = rsqrt_exact<R>(dx * dx + dy * dy + dz * dz);
-                        if (dd == R(0)) dd += R(0.001);
-                        R Fij = pair_fij<R>(a.k, a.two_sigma, dd);
-                        Real2<R> uj = a.cur.uv[j];
-                        fx += Fij * ((ui.x - uj.x) / dd);
-                        fy += Fij * ((ui.y - uj.y) / dd);
-                    }
-                }
-                if ((unsigned long long)cnt > bc.max_row) bc.max_row = cnt;
             } else {
-                bc.order_fb++;
-                int dummy_color = 0, dummy_cnt = 0;
-                bool dummy_of = false;
-                euclid_visit<R, false>(a, i, Xi, ui, keys, fx, fy, mx, my, dummy_color, nullptr, dummy_cnt, dummy_of, bc);
+                bc.order_fb++;   // long row: ordered by repeated selection instead of the register list (still exact)
             }
-        } else {
-            // fast path: statistics and sums in one unordered pass
-            const R rmax = a.two_sigma > a.color_r ? a.two_sigma : a.color_r;
-            const R rmax2 = rmax * rmax * R(1.0001);
-#pragma unroll 1
-            for (int m = 0; m < 8; ++m) {
-                bool dup = false;
-                for (int p = 0; p < m; ++p) dup |= (keys[p] == keys[m]);
-                if (dup) continue;
-                int s = a.start[keys[m]], e = a.start[keys[m] + 1];
-                for (int j = s; j < e; ++j) {
-                    Pos3<R> Xj = a.cur.X[j];
-                    R dx = Xi.x - Xj.x, dy = Xi.y - Xj.y, dz = Xi.z - Xj.z;
-                    R d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 > rmax2) continue;
-                    R d = (j == i) ? R(0) : rsqrt_exact<R>(d2);
-                    if (d != R(0) && d <= a.color_r) color++;
-                    if (!(d < a.two_sigma)) continue;
-                    R cj, sj;
-                    unsigned tf = 0;
-                    TrigLookup<R>::get(a, a.cur.hv[j].x, cj, sj, tf);
-                    mx += cj;
-                    my += sj;
-                    if (j != i) {
-                        bc.pairs++;
-                        R dd = d;
-                        if (dd == R(0)) dd += R(0.001);
-                        R Fij = pair_fij<R>(a.k, a.two_sigma, dd);
-                        Real2<R> uj = a.cur.uv[j];
-                        fx += Fij * ((ui.x - uj.x) / dd);
-                        fy += Fij * ((ui.y - uj.y) / dd);
+            // pass 2: accumulate in ascending global id, the reference's summation order
+            unsigned long long last = 0;
+            bool first = true;
+            for (int p = 0; p < cnt; ++p) {
+                int jj;
+                if (!overflow) {
+                    jj = (int)(unsigned)list[p];
+                } else {   // smallest (id, slot) key above `last` among the in-range candidates
+                    unsigned long long best = ~0ull;
+                    int m = 0, j = s_beg[0][tid], e = s_end[0][tid];
+                    for (;;) {
+                        while (j >= e && m < NRANGE - 1) {
+                            ++m;
+                            j = s_beg[m][tid];
+                            e = s_end[m][tid];
+                        }
+                        if (j >= e) break;
+                        const Pos3<R> Pj = a.cur.pos[j];
+                        const R dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                        const R d2 = dx * dx + dy * dy + dz * dz;
+                        if (d2 <= rmax2) {
+                            const R d = (j == i) ? R(0) : rsqrt_exact<R>(d2);
+                            if (d < a.two_sigma) {
+                                unsigned long long key = ((unsigned long long)(uint32_t)a.cur.aux[j].z << 32) | (unsigned)j;
+                                if ((first || key > last) && key < best) best = key;
+                            }
+                        }
+                        ++j;
                     }
+                    last = best;
+                    first = false;
+                    jj = (int)(unsigned)best;
+                }
+                const Pos3<R> Pj = a.cur.pos[jj];
+                const R dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                const R d = (jj == i) ? R(0) : rsqrt_exact<R>(dx * dx + dy * dy + dz * dz);
+                const double2 t = trig_lookup(a.trig_d, (int)Pj.w, bc.trig_fb);
+                mx += t.x;
+                my += t.y;
+                if (jj != i) {
+                    npairs++;
+                    R dd = d;
+                    if (dd == R(0)) dd += R(0.001);   // ForceHelper.cpp:59-62
+                    const R Fij = pair_fij<R>(a.k, a.two_sigma, dd);
+                    const Real2<R> uj = a.cur.uv[jj];
+                    fx += Fij * ((ui.x - uj.x) / dd);
+                    fy += Fij * ((ui.y - uj.y) / dd);
                 }
             }
         }
-        finish_particle<R>(a, i, ui, hvi.x, a.cur.id[i], fx, fy, mx, my, color, bc);
+        bc.pairs += (unsigned long long)npairs;
+
+        const Real2<R> rd = velocity_from_force<R>(a, heading, fx, fy, bc);
+        int n_new = heading_from_sum<R>(a, mx, my, (uint32_t)ai.z, bc);
+        if (MOVING) {
+            Real2<R> p = {ui.x + rd.x * a.step_size, ui.y + rd.y * a.step_size};   // Locomotion.cpp:84
+            int face, vid;
+            Pos3<R> X;
+            wrap_and_project<R>(a, ui, p, n_new, ai.y, face, vid, X, bc);
+            a.alt.pos[i] = X;
+            a.alt.uv[i] = p;
+            a.alt.aux[i] = make_int4(vid, face, ai.z, ai.w);
+            a.alt.rdot[i] = rd;
+            a.alt.color[i] = color;
+            const uint32_t key = bucket_key<R>(a, X, vid, bc);
+            a.key[i] = key;
+            a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+        } else {   // t2d_forces: report without moving
+            Real2<R> Fv = {fx, fy};
+            a.F[i] = Fv;
+            a.new_heading[i] = n_new;
+            a.cur.color[i] = color;
+        }
     }
     flush_counters(bc, a.counters);
 }
@@ -361,11 +584,13 @@ template <typename R, bool EXACT> __global__ void __launch_bounds__(128) k_neigh
 // sin n, row entry), sorted by global id, and every particle of the bucket walks the staged list in that
 // order — the reference's ascending-j summation.  Rows longer than CAP are processed in unsorted tiles
 // (counted as order fallbacks; still within 1e-9 of the reference).
+// Writes uv_new / new_heading (consumed by k_wrap_project) and rdot / colour into the resident state.
 // ---------------------------------------------------------------------------------------------------
 template <typename R> struct TableSmem {
     static constexpr int CAP = (sizeof(R) == 8) ? 2048 : 4096;   // staged neighbours per tile
     static constexpr int ECAP = 1024;                            // distinct row entries per tile
-    static constexpr size_t ELEM_BYTES = (size_t)CAP * (8 + 4 * sizeof(R) + 4 + 2);   // multiple of 16
+    // per staged element: key 8, cos 8, sin 8, ux R, uy R, id 4, entry 2  (+2 pad so that the total is a multiple of 16)
+    static constexpr size_t ELEM_BYTES = (size_t)CAP * (8 + 8 + 8 + 2 * sizeof(R) + 4 + 2 + 2);
     static constexpr size_t BYTES = ELEM_BYTES + (size_t)ECAP * 2 * sizeof(R);
 };
 
@@ -375,11 +600,11 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
     constexpr int ECAP = TableSmem<R>::ECAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);   // (id << 32) | staging index
-    R* s_ux = reinterpret_cast<R*>(s_key + CAP);
+    double* s_c = reinterpret_cast<double*>(s_key + CAP);
+    double* s_s = s_c + CAP;
+    R* s_ux = reinterpret_cast<R*>(s_s + CAP);
     R* s_uy = s_ux + CAP;
-    R* s_c = s_uy + CAP;
-    R* s_s = s_c + CAP;
-    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_s + CAP);
+    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_uy + CAP);
     unsigned short* s_ent = reinterpret_cast<unsigned short*>(s_id + CAP);
     static_assert(TableSmem<R>::ELEM_BYTES % 16 == 0, "per-entry arrays must start 16-byte aligned");
     R* s_edd = reinterpret_cast<R*>(smem_raw + TableSmem<R>::ELEM_BYTES);   // per row entry: d (0 -> 0.001) and F_ij
@@ -450,17 +675,14 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
                 for (int q = from + tid; q < to; q += THREADS) {
                     int slot = sb + q;
                     int pos = fill + (q - from);
-                    uint32_t idj = a.cur.id[slot];
+                    uint32_t idj = (uint32_t)a.cur.aux[slot].z;
                     s_key[pos] = ((unsigned long long)idj << 32) | (unsigned)pos;
                     Real2<R> uj = a.cur.uv[slot];
-                    R cj, sj;
-                    unsigned tf = 0;
-                    TrigLookup<R>::get(a, a.cur.hv[slot].x, cj, sj, tf);
-                    bc.trig_fb += tf;
+                    double2 t = trig_lookup(a.trig_d, (int)a.cur.pos[slot].w, bc.trig_fb);
                     s_ux[pos] = uj.x;
                     s_uy[pos] = uj.y;
-                    s_c[pos] = cj;
-                    s_s[pos] = sj;
+                    s_c[pos] = t.x;
+                    s_s[pos] = t.y;
                     s_id[pos] = idj;
                     s_ent[pos] = (unsigned short)ne;
                 }
@@ -496,7 +718,7 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
         };
 
         // walk the staged tile for one particle; order = s_key order when sorted, staging order otherwise
-        auto walk_tile = [&](int fill, bool sorted, uint32_t my_id, R uix, R uiy, R& fx, R& fy, R& mx, R& my) {
+        auto walk_tile = [&](int fill, bool sorted, uint32_t my_id, R uix, R uiy, R& fx, R& fy, double& mx, double& my) {
             for (int t = 0; t < fill; ++t) {
                 int p = sorted ? (int)(unsigned)s_key[t] : t;
                 mx += s_c[p];
@@ -511,7 +733,20 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
             }
         };
 
-        const int self_color = 0;   // the diagonal of the table is 0 (checked at upload), so self never counts
+        auto finish = [&](int slot, Real2<R> ui, int heading, uint32_t my_id, R fx, R fy, double mx, double my) {
+            bc.pairs += (unsigned long long)(krange - 1);
+            const Real2<R> rd = velocity_from_force<R>(a, heading, fx, fy, bc);
+            a.cur.rdot[slot] = rd;
+            a.cur.color[slot] = color_bucket;   // the table's diagonal is 0 (checked at upload): self never counts
+            Real2<R> un = {ui.x + rd.x * a.step_size, ui.y + rd.y * a.step_size};
+            a.uv_new[slot] = un;
+            if (a.write_F) {
+                Real2<R> Fv = {fx, fy};
+                a.F[slot] = Fv;
+            }
+            a.new_heading[slot] = heading_from_sum<R>(a, mx, my, my_id, bc);
+        };
+
         const int fill0 = build_tile(0);
         const bool single_tile = (fill0 == krange);
         if (!single_tile && tid == 0) bc.order_fb += (unsigned long long)(pe - pb);
@@ -527,12 +762,12 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
                 int slot = p0 + tid;
                 if (slot < pe) {
                     Real2<R> ui = a.cur.uv[slot];
-                    int2 hvi = a.cur.hv[slot];
-                    uint32_t my_id = a.cur.id[slot];
-                    R fx = 0, fy = 0, mx = 0, my = 0;
+                    int heading = (int)a.cur.pos[slot].w;
+                    uint32_t my_id = (uint32_t)a.cur.aux[slot].z;
+                    R fx = 0, fy = 0;
+                    double mx = 0, my = 0;
                     walk_tile(fill, sorted, my_id, ui.x, ui.y, fx, fy, mx, my);
-                    bc.pairs += (unsigned long long)(krange - 1);
-                    finish_particle<R>(a, slot, ui, hvi.x, my_id, fx, fy, mx, my, color_bucket - self_color, bc);
+                    finish(slot, ui, heading, my_id, fx, fy, mx, my);
                 }
             }
         } else {
@@ -540,125 +775,49 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
                 int slot = p0 + tid;
                 bool act = slot < pe;
                 Real2<R> ui = {R(0), R(0)};
-                int2 hvi = {0, 0};
+                int heading = 0;
                 uint32_t my_id = 0xffffffffu;
                 if (act) {
                     ui = a.cur.uv[slot];
-                    hvi = a.cur.hv[slot];
-                    my_id = a.cur.id[slot];
+                    heading = (int)a.cur.pos[slot].w;
+                    my_id = (uint32_t)a.cur.aux[slot].z;
                 }
-                R fx = 0, fy = 0, mx = 0, my = 0;
+                R fx = 0, fy = 0;
+                double mx = 0, my = 0;
                 for (int t0 = 0; t0 < krange;) {
                     int fill = build_tile(t0);
                     if (act) walk_tile(fill, false, my_id, ui.x, ui.y, fx, fy, mx, my);
                     if (fill == 0) break;
                     t0 += fill;
                 }
-                if (act) {
-                    bc.pairs += (unsigned long long)(krange - 1);
-                    finish_particle<R>(a, slot, ui, hvi.x, my_id, fx, fy, mx, my, color_bucket - self_color, bc);
-                }
+                if (act) finish(slot, ui, heading, my_id, fx, fy, mx, my);
             }
         }
     }
     flush_counters(bc, a.counters);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// K5 core: UV point location + lift.  The reference takes the arg-min of (2-D point-triangle distance,
-// face index) over ALL faces (CellHelper.cpp:106-117).  The containing face has distance ~1e-17, so the
-// arg-min lies among the faces whose (slightly grown) bounding box covers the point: the uniform grid
-// cell lists exactly those, in ascending face id; the same distance function decides between them.
-// ---------------------------------------------------------------------------------------------------
-template <typename R> __device__ __forceinline__ int locate_face(const DevMesh<R>& m, R px, R py, BlockCounters& bc)
-{
-    const int G = m.G;
-    int gi = (int)dev_floor<R>(px * (R)G), gj = (int)dev_floor<R>(py * (R)G);
-    gi = gi < 0 ? 0 : (gi > G - 1 ? G - 1 : gi);
-    gj = gj < 0 ? 0 : (gj > G - 1 ? G - 1 : gj);
-    const int cell = gj * G + gi;
-    int best = -1;
-    R bd = 0;
-    const int qs = m.gstart[cell], qe = m.gstart[cell + 1];
-    for (int q = qs; q < qe; ++q) {
-        int f = m.gfaces[q];
-        TriUV<R> t = m.tri[f];
-        R d = point_triangle_distance<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
-        if (best < 0 || d < bd) {
-            bd = d;
-            best = f;
-        }
-        if (bd == R(0)) break;   // ascending face id: nothing later can beat (0, f)
-    }
-    const R cover_eps = (sizeof(R) == 8) ? R(1e-9) : R(1e-5);
-    if (best < 0 || !(bd <= cover_eps)) {   // not covered by the cell list (or NaN): scan all faces like the reference
-        bc.loc_fb++;
-        best = 0;
-        TriUV<R> t0 = m.tri[0];
-        bd = point_triangle_distance<R>(px, py, t0.ax, t0.ay, t0.bx, t0.by, t0.cx, t0.cy);
-        for (int f = 1; f < m.F; ++f) {
-            TriUV<R> t = m.tri[f];
-            R d = point_triangle_distance<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy);
-            if (d < bd) {
-                bd = d;
-                best = f;
-            }
-        }
-    }
-    return best;
-}
-
-template <typename R> __device__ __forceinline__ void project_point(const DevMesh<R>& m, R px, R py, int& face, int& vid,
-                                                                    Pos3<R>& X, BlockCounters& bc)
-{
-    int f = locate_face<R>(m, px, py, bc);
-    TriUV<R> t = m.tri[f];
-    int4 tv = m.tri_vid[f];
-    Pos3<R> A = m.x3d[tv.x], B = m.x3d[tv.y], C = m.x3d[tv.z];
-    R Av[3] = {A.x, A.y, A.z}, Bv[3] = {B.x, B.y, B.z}, Cv[3] = {C.x, C.y, C.z}, Xv[3];
-    int which = lift_to_3d<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv);
-    face = f;
-    vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
-    X.x = Xv[0];
-    X.y = Xv[1];
-    X.z = Xv[2];
-    X.w = R(0);
-}
-
-template <typename R> __device__ __forceinline__ bool dev_finite(R v) { return isfinite(v); }
-
-// K4+K5: seam re-entry, projection, validation (Validation.cpp:40-72)
+// K4+K5 (table mode): seam re-entry, projection, validation (Validation.cpp:40-72), in place, + next key
 template <typename R> __global__ void __launch_bounds__(128) k_wrap_project(StepArgs<R> a)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     BlockCounters bc;
     if (i < a.N) {
-        Real2<R> old = a.cur.uv[i];
+        const Real2<R> old = a.cur.uv[i];
         Real2<R> p = a.uv_new[i];
         int n = a.new_heading[i];
-        int wraps = 0;
-        bool cap = seam_reentry<R>(old.x, old.y, p.x, p.y, n, wraps);
-        bc.wraps += wraps;
-        if (cap) {
-            bc.caps++;
-            bc.fault |= T2D_FAULT_WRAP_CAP;
-        }
-        if (!inside_square<R>(p.x, p.y)) {
-            bc.lost++;
-            bc.fault |= T2D_FAULT_LOST;
-        }
-        if (!dev_finite<R>(p.x) || !dev_finite<R>(p.y)) {
-            bc.nonfinite++;
-            bc.fault |= T2D_FAULT_NONFINITE;
-        }
+        int4 ax = a.cur.aux[i];
         int face, vid;
         Pos3<R> X;
-        project_point<R>(a.mesh, p.x, p.y, face, vid, X, bc);
+        wrap_and_project<R>(a, old, p, n, ax.y, face, vid, X, bc);
         a.cur.uv[i] = p;
-        int2 hv = {n, vid};
-        a.cur.hv[i] = hv;
-        a.cur.face[i] = face;
-        a.cur.X[i] = X;
+        a.cur.pos[i] = X;
+        ax.x = vid;
+        ax.y = face;
+        a.cur.aux[i] = ax;
+        const uint32_t key = bucket_key<R>(a, X, vid, bc);
+        a.key[i] = key;
+        a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
     }
     flush_counters(bc, a.counters);
 }
@@ -672,12 +831,13 @@ template <typename R> __global__ void __launch_bounds__(128) k_project_only(Step
         Real2<R> p = a.cur.uv[i];
         int face, vid;
         Pos3<R> X;
-        project_point<R>(a.mesh, p.x, p.y, face, vid, X, bc);
-        int2 hv = a.cur.hv[i];
-        hv.y = vid;
-        a.cur.hv[i] = hv;
-        a.cur.face[i] = face;
-        a.cur.X[i] = X;
+        project_point<R>(a.mesh, p.x, p.y, -1, face, vid, X, bc);
+        X.w = a.cur.pos[i].w;
+        a.cur.pos[i] = X;
+        int4 ax = a.cur.aux[i];
+        ax.x = vid;
+        ax.y = face;
+        a.cur.aux[i] = ax;
     }
     flush_counters(bc, a.counters);
 }
@@ -711,12 +871,9 @@ template <typename R> __global__ void __launch_bounds__(256) k_unit_vectors(Step
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     BlockCounters bc;
     if (i < N) {
-        R c, s;
-        unsigned tf = 0;
-        TrigLookup<R>::get(a, heading[i], c, s, tf);
-        bc.trig_fb += tf;
-        out[i] = c;
-        out[N + i] = s;
+        double2 t = trig_lookup(a.trig_d, heading[i], bc.trig_fb);
+        out[i] = (R)t.x;
+        out[N + i] = (R)t.y;
     }
     flush_counters(bc, a.counters);
 }
@@ -726,17 +883,30 @@ template <typename R> __global__ void __launch_bounds__(256) k_unit_vectors(Step
 // ---------------------------------------------------------------------------------------------------
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
-template <typename R> void Launch<R>::count_keys(const StepArgs<R>& a, cudaStream_t s)
+template <typename R>
+void Launch<R>::voxelize(const DevMesh<R>& m, const double org[3], double cs, double reach, const int nc[3], int nbx, int nby,
+                         unsigned long long* occ, cudaStream_t s)
 {
-    if (a.N > 0) k_count_keys<R><<<div_up(a.N, 256), 256, 0, s>>>(a);
+    int grid = div_up(m.F * 32, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_voxelize<R><<<grid, 256, 0, s>>>(m, org[0], org[1], org[2], cs, reach, nc[0], nc[1], nc[2], nbx, nby, occ);
 }
-template <typename R> void Launch<R>::reorder(const StepArgs<R>& a, cudaStream_t s)
+template <typename R> void Launch<R>::bin(const StepArgs<R>& a, cudaStream_t s)
 {
-    if (a.N > 0) k_reorder<R><<<div_up(a.N, 256), 256, 0, s>>>(a);
+    if (a.N > 0) k_bin<R><<<div_up(a.N, 256), 256, 0, s>>>(a);
 }
-template <typename R> void Launch<R>::neigh_euclid(const StepArgs<R>& a, cudaStream_t s)
+template <typename R> void Launch<R>::scatter(const StepArgs<R>& a, cudaStream_t s)
 {
-    if (a.N > 0) k_neigh_euclid<R, sizeof(R) == 8><<<div_up(a.N, 128), 128, 0, s>>>(a);
+    if (a.N > 0) k_scatter<R><<<div_up(a.N, 256), 256, 0, s>>>(a);
+}
+template <typename R> void Launch<R>::step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s)
+{
+    if (a.N <= 0) return;
+    constexpr bool EXACT = sizeof(R) == 8;
+    if (moving)
+        k_step_euclid<R, EXACT, true><<<div_up(a.N, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
+    else
+        k_step_euclid<R, EXACT, false><<<div_up(a.N, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
 }
 template <typename R> void Launch<R>::neigh_table(const StepArgs<R>& a, cudaStream_t s, int sm_count)
 {

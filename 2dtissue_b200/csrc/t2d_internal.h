@@ -15,7 +15,7 @@ namespace t2d {
 template <typename R> struct alignas(16) TriUV {   // one UV triangle, corners a,b,c
     R ax, ay, bx, by, cx, cy;
 };
-template <typename R> struct alignas(16) Pos3 {    // one 3-D vertex (w pads to 16/32 B)
+template <typename R> struct alignas(16) Pos3 {    // 3-D point; w carries the particle's heading (integer degrees)
     R x, y, z, w;
 };
 
@@ -26,7 +26,6 @@ template <typename R> struct DevMesh {
     const Pos3<R>* x3d = nullptr;            // [V]
     const int* gstart = nullptr;             // [G*G+1] CSR cell -> faces (ascending face id)
     const int* gfaces = nullptr;
-    R eucl_origin[3] = {0, 0, 0};            // 3-D cell-list origin (mesh bbox min minus one cell)
 };
 
 // per-vertex CSR of table entries that can matter: d < 2σ or d <= color_factor·σ (symmetrised by min,
@@ -38,20 +37,33 @@ struct DevCSR {
     const double* d = nullptr;    // [nnz]
 };
 
-// ---- particle state, SoA, in "slot" order (sorted by bucket key of the last binning) ------------------
+// Sparse voxel index of the 3-D cell list (Euclidean criterion).  Particles live ON the mesh surface, so the
+// set of cells that can ever hold a particle is static: the cells within half a cell diagonal of a mesh
+// triangle.  Cells are grouped in 4x4x4 blocks; a block stores a 64-bit occupancy map and the compact index
+// of its first occupied cell.  Blocks are numbered along a Morton curve, so compact cell indices — the sort
+// key of the counting sort — are spatially coherent and the bucket arrays have M ~ N entries.
+template <typename R> struct DevVox {
+    int ncx = 0, ncy = 0, ncz = 0;     // cells per axis
+    int nbx = 0, nby = 0, nbz = 0;     // blocks per axis
+    int M = 0;                         // compact cells; bucket M is the overflow bucket (cell not in the index)
+    const uint4* blocks = nullptr;     // [nbx*nby*nbz] {occupancy lo, occupancy hi, base, 0}
+    R origin[3] = {0, 0, 0};
+    R inv_cell = 0;
+};
+
+// ---- particle state, SoA, in "slot" order (sorted by bucket key) --------------------------------------
 template <typename R> struct alignas(2 * sizeof(R)) Real2 { R x, y; };
 template <typename R> struct ParticleArrays {
-    Real2<R>* uv = nullptr;      // chart coordinates (r_UV)
-    int2* hv = nullptr;          // x = heading n (integer degrees), y = nearest-vertex id (vertices_3D_active)
-    Pos3<R>* X = nullptr;        // 3-D position of the last projection (r_3D); w unused
-    int* face = nullptr;         // face of the last projection
-    uint32_t* id = nullptr;      // global particle id (RNG counter + accumulation order)
-    uint32_t* origin = nullptr;  // index in the caller's arrays
+    Pos3<R>* pos = nullptr;   // 3-D position of the last projection (r_3D) + heading n in w
+    Real2<R>* uv = nullptr;   // chart coordinates (r_UV)
+    int4* aux = nullptr;      // x = nearest-vertex id (vertices_3D_active), y = face, z = global id, w = index in the caller's arrays
+    Real2<R>* rdot = nullptr; // velocity of the last step (r_dot)
+    int* color = nullptr;     // neighbour count of the last step (particles_color)
 };
 
 struct DevCounters {   // mirrors t2d_counters' device-updated fields
     unsigned long long pairs_in_range, ties_cutoff, ties_trunc, wraps, wrap_cap_hits, order_fallbacks,
-        trig_fallbacks, locate_fallbacks, max_row, lost, nonfinite;
+        trig_fallbacks, locate_fallbacks, max_row, lost, nonfinite, cell_fallbacks;
     unsigned int fault;
     unsigned int pad;
 };
@@ -60,29 +72,27 @@ struct DevCounters {   // mirrors t2d_counters' device-updated fields
 template <typename R> struct StepArgs {
     int N = 0;
     ParticleArrays<R> cur, alt;
-    // temporaries (slot order)
-    uint32_t* key = nullptr;      // bucket key of each particle
+    uint32_t* key = nullptr;      // bucket key of each particle of `cur`
     uint32_t* rank = nullptr;     // arrival rank inside its bucket
-    int* count = nullptr;         // [M] bucket histogram (zero between steps)
-    int* start = nullptr;         // [M+1] exclusive scan
+    int* count = nullptr;         // [M+1] bucket histogram (zero between sorts)
+    int* start = nullptr;         // [M+2] exclusive scan
     int* blocksums = nullptr;
-    int M = 0;                    // number of buckets (V in table mode, hash size in Euclid mode)
-    Real2<R>* uv_new = nullptr;   // position after the Euler step, before seam re-entry
-    Real2<R>* rdot = nullptr;
-    Real2<R>* F = nullptr;
-    int* new_heading = nullptr;
-    int* color = nullptr;
+    int M = 0;                    // number of buckets (V in table mode, compact cells + 1 in Euclid mode)
+    Real2<R>* uv_new = nullptr;   // table mode: position after the Euler step, before seam re-entry
+    int* new_heading = nullptr;   // table mode / t2d_forces: heading after alignment
+    Real2<R>* F = nullptr;        // t2d_forces only
     DevCounters* counters = nullptr;
     const double2* trig_d = nullptr;   // [TRIG_N] (cos, sin) of integer degrees, built by the host's libm
     const float2* trig_f = nullptr;
+    const CrEntry* cr = nullptr;       // [181] double-double cos/sin/angle of integer degrees (cr_tables.h)
     DevMesh<R> mesh;
     DevCSR csr;
+    DevVox<R> vox;
     // parameters
-    R v0, k, two_sigma, color_r, step_size, cell_size, inv_cell;
+    R v0, k, two_sigma, color_r, step_size;
     double eta360;
     double two_sigma_d, color_r_d;   // table predicates are evaluated on doubles (the table's stored precision)
     uint64_t seed, step;
-    uint32_t hash_mask;
     int mode;
     int write_F;
     int* work_counter = nullptr;   // dynamic bucket queue for the table-mode kernel
@@ -90,12 +100,14 @@ template <typename R> struct StepArgs {
 
 // kernel launchers implemented once per precision (step_f64.cu with --fmad=false, step_f32.cu with FMA)
 template <typename R> struct Launch {
-    static void count_keys(const StepArgs<R>& a, cudaStream_t s);
-    static void reorder(const StepArgs<R>& a, cudaStream_t s);
+    static void voxelize(const DevMesh<R>& m, const double org[3], double cs, double reach, const int nc[3], int nbx, int nby,
+                         unsigned long long* occ, cudaStream_t s);   // setup: surface cells of the sparse voxel index
+    static void bin(const StepArgs<R>& a, cudaStream_t s);                      // key + rank + histogram of `cur`
+    static void scatter(const StepArgs<R>& a, cudaStream_t s);                  // cur -> alt in bucket order
+    static void step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s); // stages 2-5 fused, cur -> alt (+ next keys)
     static void neigh_table(const StepArgs<R>& a, cudaStream_t s, int sm_count);
-    static void neigh_euclid(const StepArgs<R>& a, cudaStream_t s);
-    static void wrap_project(const StepArgs<R>& a, cudaStream_t s);
-    static void project_only(const StepArgs<R>& a, cudaStream_t s);    // initial projection (get_r3d)
+    static void wrap_project(const StepArgs<R>& a, cudaStream_t s);             // table mode stages 4b-5, in place (+ next keys)
+    static void project_only(const StepArgs<R>& a, cudaStream_t s);             // initial projection (get_r3d)
     static void tiling_only(const StepArgs<R>& a, Real2<R>* uv_old, Real2<R>* uv, int* heading, int N, cudaStream_t s);
     static void unit_vectors(const StepArgs<R>& a, const int* heading, R* out, int N, cudaStream_t s);
 };
@@ -103,7 +115,7 @@ template <typename R> struct Launch {
 // precision-independent kernels (common.cu)
 void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s);   // exclusive scan, zeroes count
 int scan_blocks(int M);
-void launch_observables(const int2* hv, const void* rdot, int is_f32, int N, const double2* trig, double* out8,
+void launch_observables(const void* pos, const void* rdot, int is_f32, int N, const double2* trig, double* out8,
                         cudaStream_t s);
 
 }  // namespace t2d

@@ -30,10 +30,14 @@ sys.path.insert(0, ROOT)
 SURFACE_AREA = 451.3          # ellipsoid_x4 surface area in mesh units^2
 # algorithmic bytes per particle-step, SURVEY.md §8(d)
 B_ALG = {("f32", "table"): 144, ("f32", "euclid"): 192, ("f64", "table"): 208, ("f64", "euclid"): 280}
-# per-kernel algorithmic bytes per particle (same table, split by stage)
+# per-kernel algorithmic bytes per particle: the same table split by stage.  The fused
+# Euclid kernel is credited with the stages it replaces (K3 + K4/K5), the counting-sort scatter with K1 + K2;
+# no credit is taken for the traffic the fusion saves.
 B_KERNEL = {
-    "f32": {"count_keys": 16 + 8, "scan": 0, "reorder": 36 + 16 + 8, "neigh_force_align": 24 + 16, "wrap_project": 68},
-    "f64": {"count_keys": 32 + 8, "scan": 0, "reorder": 52 + 32 + 8, "neigh_force_align": 36 + 24, "wrap_project": 104},
+    ("f32", "euclid"): {"step_fused": (24 + 16) + 68, "scan": 0, "scatter": 16 + (36 + 16)},
+    ("f64", "euclid"): {"step_fused": (36 + 24) + 104, "scan": 0, "scatter": 16 + (52 + 32)},
+    ("f32", "table"): {"neigh_table": 24, "wrap_project": 68, "scan": 0, "scatter": 16 + 36},
+    ("f64", "table"): {"neigh_table": 36, "wrap_project": 104, "scan": 0, "scatter": 16 + 52},
 }
 
 
@@ -239,6 +243,12 @@ def main_ours(args, rank, world, local_rank):
             prof.setdefault(name, []).append(ms)
     prof = {k: statistics.median(v) for k, v in prof.items()}
 
+    if args.no_cpu_baseline:
+        if rank == 0:
+            print(json.dumps({"profiler_run": True, "ms_per_step": ms_per_step, "kernel_ms": prof}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     # end-to-end through the drop-in call with pinned host buffers
     e2e_steps = max(2, min(args.steps, 10))
     s = ctx.download(("uv", "n", "vid", "r3d"))
@@ -265,7 +275,7 @@ def main_ours(args, rank, world, local_rank):
         dom = max(prof, key=prof.get) if prof else None
         roof = None
         if dom:
-            bk = B_KERNEL[spec["dtype"]][dom] + (16 if (spec["mode"] == "euclid" and dom in ("reorder", "neigh_force_align")) else 0)
+            bk = B_KERNEL[key][dom]
             ach = bk * Nloc / (prof[dom] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None, "peak_source": peak_src, "kernel_ms": prof[dom], "alg_bytes_per_particle": bk,
@@ -300,6 +310,7 @@ def main():
     ap.add_argument("--workload", default="c4shard", choices=["c4shard", "c2", "c3"])
     ap.add_argument("--particles-per-gpu", type=int, default=0)
     ap.add_argument("--dtype", default=None, choices=[None, "f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline and e2e legs (profiler runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -17,7 +17,7 @@
  * bitmask, the analogue of the reference's exceptions:
  *     T2D_FAULT_LOST      Validation::error_lost_particles throws std::runtime_error   (Validation.cpp:66-72)
  *     T2D_FAULT_NONFINITE Validation::error_invalid_values calls std::exit(1)          (Validation.cpp:40-46)
- *     T2D_FAULT_WRAP_CAP  the seam re-entry loop (EuclideanTiling.cpp:41-68) did not terminate in 64 rounds
+ *     T2D_FAULT_WRAP_CAP  the seam re-entry loop (EuclideanTiling.cpp:41-68) did not terminate in 4096 rounds
  */
 #ifndef T2D_H
 #define T2D_H
@@ -101,7 +101,9 @@ typedef struct {
     int64_t trig_fallbacks;    /* headings outside the host-built cos/sin table */
     int64_t locate_fallbacks;  /* point locations that scanned all faces */
     int64_t max_row;           /* longest neighbour row seen */
-    int64_t reserved[5];
+    int64_t cell_fallbacks;    /* particles found outside the static 3-D cell index (kept exact via the overflow bucket) */
+    int64_t buckets;           /* number of buckets of the counting sort (mesh vertices / surface cells + 1) */
+    int64_t reserved[3];
 } t2d_counters;
 
 /* ---- lifetime -------------------------------------------------------------------------------------- */

@@ -19,7 +19,7 @@
 
 #define DEG_TO_RAD (M_PI / 180.0) /* OrientationHelper.h:26, LinearAlgebra.h */
 #define RAD_TO_DEG (180.0 / M_PI)
-#define WRAP_CAP 64
+#define WRAP_CAP 4096
 
 struct t2do_ctx {
     int V, F;

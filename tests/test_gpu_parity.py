@@ -28,6 +28,17 @@ def rel_err(a, b, scale=None):
     return float(np.max(np.abs(a - b) / s)) if a.size else 0.0
 
 
+def pre_wrap_heading(angle_ref):
+    """Heading right after alignment (OrientationHelper.cpp:67), before seam re-entry subtracts 90/270 per crossing."""
+    return np.trunc(angle_ref).astype(np.int32)
+
+
+# The CUDA path rebuilds atan2 correctly rounded at integer-degree mean angles (hd_math.cuh mean_angle_degrees_cr), so
+# headings are expected to be IDENTICAL to the reference's; the slack below only covers the (never yet observed) case
+# of glibc's atan2 not being correctly rounded on a tie input, which would be logged as a truncation tie.
+TIE_SLACK = 0.001
+
+
 def heading_mismatch_report(n_gpu, n_ref, angle_ref):
     """Headings must be identical except at truncation ties: the reference's mean angle is within 1e-9 deg of an
     integer, where the last ulp of atan2 decides.  Returns (#mismatch, #non-tie mismatch)."""
@@ -133,11 +144,14 @@ def test_step_fp64_vs_reference_golden(t2d, chart, oracle, hop_table, metric_tab
         has_noise = ("eta%d" % s) in z.files
         # the oracle (bit-identical to the reference, test_oracle_vs_reference.py) gives the pre-truncation angle
         o = oracle.step(uv, n, vid, r3d, v0, k, sigma, h, mode=mode)
+        pre = pre_wrap_heading(o["angle"])
+        nbad, nontie = heading_mismatch_report(nh, pre, o["angle"])
+        assert nontie == 0, "heading differs away from a truncation tie"
+        total_bad += nbad
+        good = nh == pre
+        assert np.array_equal(out["n"][good], o["n"][good])
         if not has_noise:
-            nbad, nontie = heading_mismatch_report(nh, o["n"], o["angle"])
-            assert nontie == 0, "heading differs away from a truncation tie"
-            total_bad += nbad
-        good = (nh == o["n"]) if not has_noise else np.ones(N, dtype=bool)
+            assert np.array_equal(out["n"][good], z["n%d" % s][good]), "headings after seam re-entry vs the reference"
         # particles whose heading matched must match the reference everywhere else, bit-exact on indices
         ref_uv, ref_vid, ref_r3d = o["uv"], o["vid"], o["r3d"]
         g2 = np.concatenate([good, good])
@@ -152,8 +166,8 @@ def test_step_fp64_vs_reference_golden(t2d, chart, oracle, hop_table, metric_tab
             assert np.array_equal(out["uv"][g2], z["uv%d" % s][g2])
             assert np.array_equal(out["r3d"][g3], z["r3d%d" % s][g3])
     c = ctx.counters()
-    assert c["order_fallbacks"] == 0 and c["trig_fallbacks"] == 0 and c["locate_fallbacks"] == 0
-    assert total_bad <= 0.02 * N * int(z["nsteps"]), "too many truncation-tie mismatches"
+    assert c["order_fallbacks"] == 0 and c["trig_fallbacks"] == 0 and c["locate_fallbacks"] == 0 and c["cell_fallbacks"] == 0
+    assert total_bad <= TIE_SLACK * N * int(z["nsteps"]) + 1, "too many truncation-tie mismatches"
     print("%s: heading tie mismatches %d / %d, counters %s" % (name, total_bad, N * int(z["nsteps"]), c))
 
 
@@ -178,8 +192,9 @@ def test_step_fp32_fast_path(t2d, chart, hop_table, metric_tab, name):
     ctx.step(1)
     out = ctx.download()
     speed = np.hypot(z["rdot1"][:N], z["rdot1"][N:])
-    ok = np.abs(nh - z["n1"]) <= 1
-    assert ok.mean() > 0.97
+    # headings are accumulated in double and truncated by the same correctly-rounded rule on both precision paths:
+    # they equal the reference's wherever the fp32 neighbour set and seam crossings agree
+    assert (out["n"] == z["n1"]).mean() > 0.97
     sc = np.maximum(np.concatenate([speed, speed]), 1.0)
     assert rel_err(out["rdot"], z["rdot1"], sc) <= 20 * TOL32     # |F| sums of ~1e3-magnitude terms in fp32
     # positions: compare particles that did not wrap differently
@@ -215,7 +230,7 @@ def test_step_vs_oracle_seeded(t2d, chart, oracle, hop_table, mode, N, sigma):
         g = ctx.download()
         assert fault == o["fault"]
         nbad, nontie = heading_mismatch_report(g["n"], o["n"], o["angle"])
-        assert nontie == 0 and nbad <= 0.02 * N
+        assert nontie == 0 and nbad <= TIE_SLACK * N + 1
         assert np.array_equal(g["color"], o["color"])
         assert np.array_equal(g["rdot"], o["rdot"])
         good = g["n"] == o["n"]
@@ -223,7 +238,7 @@ def test_step_vs_oracle_seeded(t2d, chart, oracle, hop_table, mode, N, sigma):
         assert np.array_equal(g["uv"][np.concatenate([good, good])], o["uv"][np.concatenate([good, good])])
         uv_c, n_c, vid_c, r3d_c = o["uv"], o["n"], o["vid"], o["r3d"]
     c = ctx.counters()
-    assert c["pairs_in_range"] > 0 and c["order_fallbacks"] == 0
+    assert c["pairs_in_range"] > 0 and c["order_fallbacks"] == 0 and c["cell_fallbacks"] == 0
 
 
 def test_noise_parity_with_oracle(t2d, chart, oracle):
@@ -239,7 +254,7 @@ def test_noise_parity_with_oracle(t2d, chart, oracle):
     o = oracle.step(uv, n, s0["vid"], s0["r3d"], 0.1, 1.0, sigma, 0.001, eta=eta, seed=seed, mode=1, step_index=17)
     # identical Philox stream on both sides -> identical noisy headings except where the noiseless mean angle ties
     bad = np.nonzero(g["n"] != o["n"])[0]
-    assert all(abs(o["angle"][i] - np.rint(o["angle"][i])) < 1e-9 for i in bad) and len(bad) <= 0.02 * N
+    assert all(abs(o["angle"][i] - np.rint(o["angle"][i])) < 1e-9 for i in bad) and len(bad) <= TIE_SLACK * N + 1
     assert len(np.unique(g["n"] - n)) > 50      # the noise really is per particle
 
 
@@ -299,7 +314,7 @@ def test_driver_mirror_readme_config(t2d, chart, oracle, hop_table):
         phi_o = oracle.observables(g["n"], g["rdot"])[0]
         assert abs(system.order_parameter - phi_o) < 1e-12
         st = dict(uv=g["uv"], n=g["n"], vid=g["vid"], r3d=g["r3d"])      # follow the GPU trajectory
-    assert len(sim.get_order_parameter()) == steps and ties <= 0.02 * N * steps
+    assert len(sim.get_order_parameter()) == steps and ties <= TIE_SLACK * N * steps + 1
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -322,7 +337,7 @@ def test_full_size_properties_1M(t2d, chart, precision):
     s = ctx.download()
     assert np.all((s["uv"] >= 0) & (s["uv"] <= 1))                           # nobody lost (Validation.cpp:66-72)
     assert np.all(np.isfinite(s["uv"])) and np.all(np.isfinite(s["r3d"]))
-    assert np.all((s["n"] >= -270 * 3) & (s["n"] < 360))
+    assert np.all((s["n"] >= -270 * 4) & (s["n"] <= 360))   # 360: a tiny negative mean angle + 360.0 rounds to 360.0
     assert np.all((s["vid"] >= 0) & (s["vid"] < ctx.V)) and np.all((s["face"] >= 0) & (s["face"] < ctx.F))
     # the lifted point lies in the bounding box of its face's corners, and the stored vertex is a corner
     faces, x3d = chart["faces"], chart["x3d"]
@@ -336,7 +351,7 @@ def test_full_size_properties_1M(t2d, chart, precision):
     obs = ctx.observables()
     assert 0 <= obs["phi"] <= 1 and obs["mean_speed"] >= 0.1 - 1e-6
     c = ctx.counters()
-    assert c["wrap_cap_hits"] == 0 and c["locate_fallbacks"] == 0
+    assert c["wrap_cap_hits"] == 0 and c["locate_fallbacks"] == 0 and c["cell_fallbacks"] == 0
 
 
 def test_table_mode_1M_hop_table_runs(t2d, chart, hop_table):

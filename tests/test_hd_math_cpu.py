@@ -76,3 +76,19 @@ def test_inside_and_fij(hd_lib, oracle_mod):
     oracle_mod.lib().t2do_repulsive_adhesion(10.0, 1.4166666666666667, 0.953489, 1.0, 0.75, 1.0, 0.0, _d(out))
     assert hd_lib.hd_pair_fij(10.0, 2 * 1.4166666666666667, 0.953489) / 0.953489 == out[0] or \
         abs(hd_lib.hd_pair_fij(10.0, 2 * 1.4166666666666667, 0.953489) * (1.0 / 0.953489) - out[0]) < 1e-15
+
+
+def test_mean_angle_correctly_rounded_matches_glibc_pipeline(hd_lib):
+    """The fp64 heading path rebuilds atan2 correctly rounded (hd_math.cuh mean_angle_degrees_cr) because the
+    reference truncates the mean angle to int and aligned / isolated particles sit exactly on integer degrees.
+    Exhaustive over the tie families + 2M random neighbour sets: the truncated heading must equal the glibc
+    pipeline's (what the reference executes) in every case."""
+    hd_lib.hd_cr_selfcheck.restype = C.c_longlong
+    for family in (0, 1, 2):
+        sets, ties, val = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        bad = hd_lib.hd_cr_selfcheck(family, C.byref(sets), C.byref(ties), C.byref(val))
+        print("family %d: %d sets, %d ties, %d angle doubles differ, %d headings differ" %
+              (family, sets.value, ties.value, val.value, bad))
+        assert bad == 0
+        if family < 2:
+            assert ties.value > 0.5 * sets.value
