@@ -106,6 +106,47 @@ template <typename R> __device__ __forceinline__ int vox_index(const DevVox<R>& 
     return (int)e.z + __popcll(bm & ((1ull << bit) - 1ull));
 }
 
+// x-run lookup for the stencil: cells (x0, y, z) and (x0 + 1, y, z).  Compact indices are x-fastest inside a 4x4x4
+// block, so when both cells sit in one block their particles form ONE contiguous range
+// [start[i0], start[i0 + o0 + o1]); otherwise the two cells are looked up separately.  Appends the non-empty
+// ranges to this thread's column of the shared range table.
+template <typename R, int NT>
+__device__ __forceinline__ void vox_row_ranges(const StepArgs<R>& a, int x0, int y, int z, int (*s_beg)[NT], int (*s_end)[NT],
+                                               int tid, int& nr)
+{
+    const DevVox<R>& vx = a.vox;
+    if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz) return;
+    if ((x0 & 3) != 3 && (unsigned)x0 < (unsigned)(vx.ncx - 1)) {
+        const int b = ((z >> 2) * vx.nby + (y >> 2)) * vx.nbx + (x0 >> 2);
+        const uint4 e = __ldg(&vx.blocks[b]);
+        const unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x0 & 3);
+        const unsigned long long bm = ((unsigned long long)e.y << 32) | e.x;
+        const int occ = (int)((bm >> bit) & 3ull);   // bit 0: cell x0, bit 1: cell x0 + 1
+        if (occ) {
+            const int i0 = (int)e.z + __popcll(bm & ((1ull << bit) - 1ull));
+            const int sb = a.start[i0], se = a.start[i0 + (occ & 1) + (occ >> 1)];
+            if (se > sb) {
+                s_beg[nr][tid] = sb;
+                s_end[nr][tid] = se;
+                nr++;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int idx = vox_index<R>(vx, x0 + q, y, z);
+            if (idx >= 0) {
+                const int sb = a.start[idx], se = a.start[idx + 1];
+                if (se > sb) {
+                    s_beg[nr][tid] = sb;
+                    s_end[nr][tid] = se;
+                    nr++;
+                }
+            }
+        }
+    }
+}
+
 // bucket key of a particle: nearest-vertex id (table criterion) or compact 3-D cell (Euclidean criterion)
 template <typename R> __device__ __forceinline__ uint32_t bucket_key(const StepArgs<R>& a, const Pos3<R>& X, int vid, BlockCounters& bc)
 {
@@ -378,11 +419,13 @@ __device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> 
 constexpr int EUCLID_KMAX = 48;
 constexpr int STEP_THREADS = 128;
 constexpr int NRANGE = 9;
+constexpr int HITCAP = 24;   // in-range neighbours recorded per thread before falling back to in-place handling
 
-template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__(STEP_THREADS) k_step_euclid(StepArgs<R> a)
+template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, EXACT ? 4 : 8) k_step_euclid(StepArgs<R> a)
 {
     __shared__ int s_beg[NRANGE][STEP_THREADS];
     __shared__ int s_end[NRANGE][STEP_THREADS];
+    __shared__ int s_hit[EXACT ? 1 : HITCAP][STEP_THREADS];
     const int tid = threadIdx.x;
     const int i = blockIdx.x * STEP_THREADS + tid;
     BlockCounters bc;
@@ -391,23 +434,21 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
         const Real2<R> ui = a.cur.uv[i];
         const int4 ai = a.cur.aux[i];
         const int heading = (int)Pi.w;
+        int nr = 0;   // non-empty candidate ranges of this particle
         {
             int c[3], side[3];
             cell_coords<R>(a.vox, Pi, c, side);
+            const int x0 = side[0] < 0 ? c[0] - 1 : c[0];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                int idx = vox_index<R>(a.vox, c[0] + ((m & 1) ? side[0] : 0), c[1] + ((m & 2) ? side[1] : 0),
-                                       c[2] + ((m & 4) ? side[2] : 0));
-                int s = 0, e = 0;
-                if (idx >= 0) {
-                    s = a.start[idx];
-                    e = a.start[idx + 1];
-                }
-                s_beg[m][tid] = s;
-                s_end[m][tid] = e;
+            for (int m = 0; m < 4; ++m)
+                vox_row_ranges<R, STEP_THREADS>(a, x0, c[1] + ((m & 1) ? side[1] : 0), c[2] + ((m & 2) ? side[2] : 0), s_beg, s_end,
+                                                tid, nr);
+            const int ob = a.start[a.vox.M], oe = a.start[a.vox.M + 1];   // overflow bucket: normally empty
+            if (oe > ob) {
+                s_beg[nr][tid] = ob;
+                s_end[nr][tid] = oe;
+                nr++;
             }
-            s_beg[8][tid] = a.start[a.vox.M];
-            s_end[8][tid] = a.start[a.vox.M + 1];
         }
         const R rmax = a.two_sigma > a.color_r ? a.two_sigma : a.color_r;
         const R rmax2 = rmax * rmax * R(1.0001);
@@ -417,42 +458,66 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
         int npairs = 0;
 
         if constexpr (!EXACT) {
-            // fast path: predicates on squared distances, one rsqrt per in-range pair, sums in visiting order
+            // fast path: predicates on squared distances, one rsqrt per in-range pair, sums in visiting order.
+            // Phase 1 walks all candidates with a tight distance test and only RECORDS the in-range ones (a
+            // third of them) in a per-thread shared-memory list; phase 2 runs the expensive pair body over that
+            // dense list, so that lanes are not dragged through it for the other lanes' hits.
             const float r2s = a.two_sigma * a.two_sigma, r2c = a.color_r * a.color_r;
             const float inv2s = 1.0f / a.two_sigma;
-            int m = 0, j = s_beg[0][tid], e = s_end[0][tid];
-            for (;;) {
-                while (j >= e && m < NRANGE - 1) {
-                    ++m;
-                    j = s_beg[m][tid];
-                    e = s_end[m][tid];
+            auto pair_body = [&](int j, const Pos3<R>& Pj, float d2) {
+                const double2 t = trig_lookup(a.trig_d, (int)Pj.w, bc.trig_fb);
+                mx += t.x;
+                my += t.y;
+                if (j != i) {
+                    npairs++;
+                    float rinv = rsqrtf(d2), d = d2 * rinv;
+                    if (d2 == 0.0f) {   // coincident particles: d := 0.001 (ForceHelper.cpp:59-62)
+                        d = 0.001f;
+                        rinv = 1000.0f;
+                    }
+                    const float g = -a.k * (a.two_sigma - d) * inv2s * rinv;   // F_ij / d
+                    const Real2<R> uj = a.cur.uv[j];
+                    fx += g * (ui.x - uj.x);
+                    fy += g * (ui.y - uj.y);
                 }
-                if (j >= e) break;
-                const Pos3<R> Pj = a.cur.pos[j];
-                const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
-                const float d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 <= rmax2) {
-                    const bool other = (j != i);
-                    color += (other && d2 > 0.0f && d2 <= r2c) ? 1 : 0;   // _2DTissue::count_particle_neighbors
-                    if (d2 < r2s) {
-                        const double2 t = trig_lookup(a.trig_d, (int)Pj.w, bc.trig_fb);
-                        mx += t.x;
-                        my += t.y;
-                        if (other) {
-                            npairs++;
-                            float rinv = rsqrtf(d2), d = d2 * rinv;
-                            if (d2 == 0.0f) {   // coincident particles: d := 0.001 (ForceHelper.cpp:59-62)
-                                d = 0.001f;
-                                rinv = 1000.0f;
-                            }
-                            const float g = -a.k * (a.two_sigma - d) * inv2s * rinv;   // F_ij / d
-                            const Real2<R> uj = a.cur.uv[j];
-                            fx += g * (ui.x - uj.x);
-                            fy += g * (ui.y - uj.y);
-                        }
+            };
+            int nhit = 0;
+            int m = 0, jn = 0, e = 0;
+            bool have = nr > 0;
+            Pos3<R> Pn = Pi;
+            if (have) {
+                jn = s_beg[0][tid];
+                e = s_end[0][tid];
+                Pn = a.cur.pos[jn];
+            }
+            while (have) {
+                const int j = jn;
+                const Pos3<R> Pj = Pn;
+                // advance and issue the next candidate's load before working on this one
+                if (++jn >= e) {
+                    if (++m < nr) {
+                        jn = s_beg[m][tid];
+                        e = s_end[m][tid];
+                    } else {
+                        have = false;
                     }
                 }
-                ++j;
+                if (have) Pn = a.cur.pos[jn];
+                const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                color += (j != i && d2 > 0.0f && d2 <= r2c) ? 1 : 0;   // _2DTissue::count_particle_neighbors
+                if (d2 < r2s) {
+                    if (nhit < HITCAP)
+                        s_hit[nhit++][tid] = j;
+                    else
+                        pair_body(j, Pj, d2);   // list full: handle in place
+                }
+            }
+            for (int t = 0; t < nhit; ++t) {
+                const int j = s_hit[t][tid];
+                const Pos3<R> Pj = a.cur.pos[j];
+                const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                pair_body(j, Pj, dx * dx + dy * dy + dz * dz);
             }
         }
 
@@ -462,9 +527,9 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
             bool overflow = false;
             // pass 1: every candidate once: colour, cutoff ties, list of in-range neighbours
             {
-                int m = 0, j = s_beg[0][tid], e = s_end[0][tid];
+                int m = 0, j = nr > 0 ? s_beg[0][tid] : 0, e = nr > 0 ? s_end[0][tid] : 0;
                 for (;;) {
-                    while (j >= e && m < NRANGE - 1) {
+                    while (j >= e && m < nr - 1) {
                         ++m;
                         j = s_beg[m][tid];
                         e = s_end[m][tid];
@@ -509,9 +574,9 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
                     jj = (int)(unsigned)list[p];
                 } else {   // smallest (id, slot) key above `last` among the in-range candidates
                     unsigned long long best = ~0ull;
-                    int m = 0, j = s_beg[0][tid], e = s_end[0][tid];
+                    int m = 0, j = nr > 0 ? s_beg[0][tid] : 0, e = nr > 0 ? s_end[0][tid] : 0;
                     for (;;) {
-                        while (j >= e && m < NRANGE - 1) {
+                        while (j >= e && m < nr - 1) {
                             ++m;
                             j = s_beg[m][tid];
                             e = s_end[m][tid];
