@@ -40,7 +40,8 @@ SYMBOLS = [
     "t2d_particle_count", "t2d_step", "t2d_step_host", "t2d_observables", "t2d_get_counters", "t2d_reset_counters",
     "t2d_get_step", "t2d_set_step", "t2d_set_params", "t2d_get_r3d", "t2d_tiling", "t2d_angles_to_unit_vectors",
     "t2d_forces", "t2d_build_hop_table", "t2d_last_step_ms", "t2d_profile_step", "t2d_pinned_alloc", "t2d_pinned_free",
-    "t2d_comm_unique_id", "t2d_comm_init", "t2d_comm_destroy",
+    "t2d_comm_unique_id", "t2d_comm_init", "t2d_comm_init_local", "t2d_step_local", "t2d_comm_destroy", "t2d_owned_count",
+    "t2d_download_ids",
 ]
 
 _lib = None
@@ -89,5 +90,10 @@ def load():
     L.t2d_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     L.t2d_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte), dp]
     L.t2d_comm_destroy.argtypes = [vp]
+    L.t2d_comm_init_local.argtypes = [C.POINTER(vp), C.c_int, dp]
+    L.t2d_step_local.argtypes = [C.POINTER(vp), C.c_int, C.c_int32]
+    L.t2d_owned_count.argtypes = [vp]
+    L.t2d_owned_count.restype = C.c_int32
+    L.t2d_download_ids.argtypes = [vp, up]
     _lib = L
     return L

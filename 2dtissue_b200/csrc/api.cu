@@ -17,6 +17,13 @@
 
 namespace t2d {
 int launch_hop_table(int V, const int* d_adj_start, const int* d_adj, uint8_t* out_dev, int sm_count, cudaStream_t s);
+// comm.cu: NCCL transport (libnccl opened at run time)
+struct NcclLink;
+int nccl_unique_id(uint8_t* out, std::string* err);
+NcclLink* nccl_link_create(int rank, int world, const uint8_t* id_bytes, std::string* err);
+void nccl_link_destroy(NcclLink* l);
+int nccl_exchange(NcclLink* l, const void* send_left, void* recv_left, const void* send_right, void* recv_right, size_t bytes,
+                  cudaStream_t s, std::string* err);
 }
 
 using namespace t2d;
@@ -81,6 +88,20 @@ struct EngineBase {
     virtual int forces(double* F, int* new_heading, int* color) = 0;
     virtual int hop_table(uint8_t* out) = 0;
     virtual int profile_step(const char** names, double* ms, int cap) = 0;
+    // slab mode
+    virtual int comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* left, EngineBase* right) = 0;
+    virtual int comm_destroy() = 0;
+    virtual void comm_phase1() = 0;                 // (advance +) classify + pack into the send buffers
+    virtual void comm_local_send() = 0;             // local group: copy the messages into the neighbours' receive buffers
+    virtual void comm_phase2() = 0;                 // append what arrived + counting sort
+    virtual int comm_finish() = 0;                  // synchronise, return the fault mask
+    virtual int owned_count() = 0;
+    virtual int download_ids(uint32_t* ids) = 0;
+    virtual unsigned char* comm_recv_buffer(int dir) = 0;
+    virtual cudaEvent_t comm_event(int which) = 0;   // 0: messages sent, 1: messages consumed
+    virtual bool comm_is_local() const = 0;
+    virtual bool halo_ready() const = 0;
+    virtual int device() const = 0;
     int N = 0;
     int64_t step_index = 0;
     double last_step_ms = 0;
@@ -126,8 +147,22 @@ template <typename R> class Engine : public EngineBase {
     int forces(double* F, int* new_heading, int* color) override;
     int hop_table(uint8_t* out) override;
     int profile_step(const char** names, double* ms, int cap) override;
+    int comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* left, EngineBase* right) override;
+    int comm_destroy() override;
+    void comm_phase1() override;
+    void comm_local_send() override;
+    void comm_phase2() override;
+    int comm_finish() override;
+    int owned_count() override;
+    int download_ids(uint32_t* ids) override;
+    unsigned char* comm_recv_buffer(int dir) override { return comm_recv_[dir].p; }
+    cudaEvent_t comm_event(int which) override { return which == 0 ? ev_sent_ : ev_consumed_; }
+    bool comm_is_local() const override { return comm_on_ && !link_; }
+    bool halo_ready() const override { return halo_valid_; }
+    int device() const override { return device_; }
 
   private:
+    int compact_owned();   // slab mode: stable compaction offsets of the owned particles; returns their number
     void upload_chart();
     void build_csr();
     void build_vox();
@@ -147,6 +182,17 @@ template <typename R> class Engine : public EngineBase {
     HostChart chart_;
     int capacity_ = 0;
     bool sorted_ = false;   // `cur` is in bucket order and start[] is valid
+    // slab mode
+    bool comm_on_ = false, halo_valid_ = false;
+    int resident_ = 0;   // resident slots (owned + halo) at the last compaction
+    NcclLink* link_ = nullptr;
+    EngineBase* peer_[2] = {nullptr, nullptr};
+    size_t msg_bytes_ = 0;
+    DevBuf<unsigned char> comm_send_[2], comm_recv_[2];
+    DevBuf<DevCommState> comm_state_;
+    DevBuf<int> d_cflag_, d_coff_, d_cblk_;
+    cudaEvent_t ev_sent_ = nullptr, ev_consumed_ = nullptr;
+    std::vector<double> cuts_;
     double vox_sigma_ = -1, vox_color_ = -1;
     int64_t launches_ = 0, steps_ = 0;
 
@@ -262,6 +308,7 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
 
 template <typename R> Engine<R>::~Engine()
 {
+    comm_destroy();
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -607,20 +654,65 @@ int Engine<R>::set_state(int N, const double* uv, const int* heading, const int*
     CK(cudaSetDevice(device_));
     this->N = N;
     A_.N = N;
+    if (comm_on_) {   // project_only / ingest run on the host-known count; the slab count is installed afterwards
+        A_.comm.on = 0;
+    }
     ingest(N, uv, heading, vid, r3d, ids, A_.cur);
     if (project) {
         Launch<R>::project_only(A_, stream_);
         launches_++;
     }
-    resort(false);
+    if (comm_on_) {
+        A_.comm.on = 1;
+        DevCommState st{N, N};
+        CK(cudaMemcpyAsync(comm_state_.p, &st, sizeof(st), cudaMemcpyHostToDevice, stream_));
+        CK(cudaMemsetAsync(d_count_.p, 0, d_count_.n * sizeof(int), stream_));
+        halo_valid_ = false;   // the first step starts with a pack + exchange + sort of the uploaded particles
+        sorted_ = false;
+    } else {
+        resort(false);
+    }
     CK(cudaStreamSynchronize(stream_));
     CK(cudaGetLastError());
     return 0;
 }
 
+// slab mode: stable compaction of the owned particles (halo copies are skipped): offsets in d_coff_
+template <typename R> int Engine<R>::compact_owned()
+{
+    DevCommState st;
+    CK(cudaMemcpyAsync(&st, comm_state_.p, sizeof(st), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    const int n = st.n;
+    IoLaunch<R>::owned_flags(n, A_.cur, d_cflag_.p, stream_);
+    launch_scan(d_cflag_.p, d_coff_.p, d_cblk_.p, n, stream_);
+    launches_ += 4;
+    int owned = 0;
+    CK(cudaMemcpyAsync(&owned, d_coff_.p + n, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    resident_ = n;
+    this->N = owned;
+    return owned;
+}
+
+template <typename R> int Engine<R>::owned_count()
+{
+    CK(cudaSetDevice(device_));
+    if (!comm_on_) return this->N;
+    if (!sorted_) throw CudaError{"slab mode: step at least once (or call t2d_step(ctx, 0)) before downloading"};
+    return compact_owned();
+}
+
 template <typename R> int Engine<R>::download(double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, int* face)
 {
     CK(cudaSetDevice(device_));
+    int resident = this->N;
+    const int* offsets = nullptr;
+    if (comm_on_) {
+        owned_count();
+        resident = resident_;
+        offsets = d_coff_.p;
+    }
     const size_t N = (size_t)this->N;
     unsigned char* base = d_stage_out_.p;
     size_t off = 0;
@@ -637,7 +729,7 @@ template <typename R> int Engine<R>::download(double* uv, int* heading, int* vid
     if (rdot) o.rdot = (double*)take(16 * N);
     if (color) o.color = (int*)take(4 * N);
     if (face) o.face = (int*)take(4 * N);
-    IoLaunch<R>::egest((int)N, A_.cur, A_.F, A_.new_heading, o, stream_);
+    IoLaunch<R>::egest(resident, (int)N, offsets, A_.cur, A_.F, A_.new_heading, o, stream_);
     launches_++;
     if (uv) CK(cudaMemcpyAsync(uv, o.uv, 16 * N, cudaMemcpyDeviceToHost, stream_));
     if (heading) CK(cudaMemcpyAsync(heading, o.heading, 4 * N, cudaMemcpyDeviceToHost, stream_));
@@ -648,6 +740,160 @@ template <typename R> int Engine<R>::download(double* uv, int* heading, int* vid
     if (face) CK(cudaMemcpyAsync(face, o.face, 4 * N, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     return 0;
+}
+
+template <typename R> int Engine<R>::download_ids(uint32_t* ids)
+{
+    CK(cudaSetDevice(device_));
+    int resident = this->N;
+    const int* offsets = nullptr;
+    if (comm_on_) {
+        owned_count();
+        resident = resident_;
+        offsets = d_coff_.p;
+    }
+    const size_t N = (size_t)this->N;
+    HostViewOut o{};
+    o.ids = (uint32_t*)d_stage_out_.p;
+    IoLaunch<R>::egest(resident, (int)N, offsets, A_.cur, A_.F, A_.new_heading, o, stream_);
+    launches_++;
+    CK(cudaMemcpyAsync(ids, o.ids, 4 * N, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    return 0;
+}
+
+// ---- slab mode -----------------------------------------------------------------------------------------
+template <typename R>
+int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* left, EngineBase* right)
+{
+    CK(cudaSetDevice(device_));
+    if (P_.neigh_mode != T2D_NEIGH_EUCLID) throw CudaError{"slab mode supports the Euclidean criterion only"};
+    if (world < 1 || rank < 0 || rank >= world) throw CudaError{"bad rank / world"};
+    if (comm_on_) comm_destroy();
+    for (int r = 0; r + 2 < world; ++r)
+        if (!(cuts[r] < cuts[r + 1])) throw CudaError{"slab cuts must be ascending"};
+    cuts_.assign(cuts, cuts + (world > 1 ? world - 1 : 0));
+    const double big = 1e30;
+    auto cut = [&](int k) { return k < 0 ? -big : (k >= world - 1 ? big : cuts_[k]); };   // boundary between slab k and k+1
+    const double rmax = std::max(2 * P_.sigma, P_.color_factor * P_.sigma);
+    A_.comm.rank = rank;
+    A_.comm.world = world;
+    A_.comm.lo = (R)cut(rank - 1);
+    A_.comm.hi = (R)cut(rank);
+    A_.comm.lo2 = (R)cut(rank - 2);
+    A_.comm.hi2 = (R)cut(rank + 1);
+    A_.comm.halo = (R)(rmax * (1.0 + (sizeof(R) == 8 ? 1e-9 : 1e-3)));
+    if (world > 1 && (double)A_.comm.hi - (double)A_.comm.lo < 4.0 * rmax && rank > 0 && rank < world - 1)
+        throw CudaError{"slab narrower than 4 r_max"};
+    A_.comm.mig_cap = std::max(1024, capacity_ / 64);
+    A_.comm.ghost_cap = std::max(4096, capacity_ / 16);
+    A_.comm.capacity = capacity_;
+    msg_bytes_ = Launch<R>::comm_message_bytes(A_.comm.mig_cap, A_.comm.ghost_cap);
+    for (int d = 0; d < 2; ++d) {
+        comm_send_[d].alloc(msg_bytes_);
+        comm_recv_[d].alloc(msg_bytes_);
+        CK(cudaMemsetAsync(comm_send_[d].p, 0, 16, stream_));
+        CK(cudaMemsetAsync(comm_recv_[d].p, 0, 16, stream_));
+        A_.comm.send[d] = comm_send_[d].p;
+        A_.comm.recv[d] = comm_recv_[d].p;
+    }
+    comm_state_.alloc(1);
+    DevCommState st{this->N, this->N};
+    CK(cudaMemcpyAsync(comm_state_.p, &st, sizeof(st), cudaMemcpyHostToDevice, stream_));
+    A_.comm.state = comm_state_.p;
+    d_cflag_.alloc((size_t)capacity_ + 8);
+    d_coff_.alloc((size_t)capacity_ + 8);
+    d_cblk_.alloc((size_t)scan_blocks(capacity_) + 8);
+    CK(cudaEventCreateWithFlags(&ev_sent_, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_consumed_, cudaEventDisableTiming));
+    CK(cudaStreamSynchronize(stream_));
+    peer_[0] = left;
+    peer_[1] = right;
+    if (id) {
+        std::string err;
+        link_ = nccl_link_create(rank, world, id, &err);
+        if (!link_) throw CudaError{err};
+    }
+    A_.comm.on = 1;
+    comm_on_ = true;
+    halo_valid_ = false;
+    sorted_ = false;
+    return 0;
+}
+
+template <typename R> int Engine<R>::comm_destroy()
+{
+    if (!comm_on_) return 0;
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    if (link_) nccl_link_destroy(link_);
+    link_ = nullptr;
+    if (ev_sent_) cudaEventDestroy(ev_sent_);
+    if (ev_consumed_) cudaEventDestroy(ev_consumed_);
+    ev_sent_ = ev_consumed_ = nullptr;
+    A_.comm.on = 0;
+    comm_on_ = false;
+    return 0;
+}
+
+// advance one step (unless the halo has not been built yet: first call after an upload) and pack the messages
+template <typename R> void Engine<R>::comm_phase1()
+{
+    CK(cudaSetDevice(device_));
+    for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(comm_send_[d].p, 0, 16, stream_));
+    if (halo_valid_) {
+        A_.step = (uint64_t)step_index;
+        Launch<R>::step_euclid(A_, true, stream_);   // cur -> alt
+        std::swap(A_.cur, A_.alt);
+        launches_++;
+    }
+    Launch<R>::comm_pack(A_, stream_);
+    launches_++;
+}
+
+template <typename R> void Engine<R>::comm_local_send()
+{
+    CK(cudaSetDevice(device_));
+    for (int d = 0; d < 2; ++d) {
+        EngineBase* p = peer_[d];
+        if (!p) continue;
+        CK(cudaStreamWaitEvent(stream_, p->comm_event(1), 0));   // the neighbour has consumed the previous message
+        CK(cudaMemcpyPeerAsync(p->comm_recv_buffer(1 - d), p->device(), comm_send_[d].p, device_, msg_bytes_, stream_));
+    }
+    CK(cudaEventRecord(ev_sent_, stream_));
+}
+
+template <typename R> void Engine<R>::comm_phase2()
+{
+    CK(cudaSetDevice(device_));
+    if (link_) {
+        std::string err;
+        if (nccl_exchange(link_, comm_send_[0].p, comm_recv_[0].p, comm_send_[1].p, comm_recv_[1].p, msg_bytes_, stream_, &err) != 0)
+            throw CudaError{err};
+    } else {
+        for (int d = 0; d < 2; ++d)
+            if (peer_[d]) CK(cudaStreamWaitEvent(stream_, peer_[d]->comm_event(0), 0));
+    }
+    Launch<R>::comm_unpack(A_, stream_);
+    launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
+    Launch<R>::scatter(A_, stream_);
+    std::swap(A_.cur, A_.alt);
+    launches_ += 5;
+    CK(cudaEventRecord(ev_consumed_, stream_));
+    if (halo_valid_) {
+        step_index++;
+        steps_++;
+    }
+    halo_valid_ = true;
+    sorted_ = true;
+}
+
+template <typename R> int Engine<R>::comm_finish()
+{
+    CK(cudaSetDevice(device_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    return read_fault();
 }
 
 template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int* nev)
@@ -703,6 +949,25 @@ template <typename R> int Engine<R>::read_fault()
 template <typename R> int Engine<R>::step(int nsteps)
 {
     CK(cudaSetDevice(device_));
+    if (comm_on_) {
+        if (!link_) throw CudaError{"local slab groups are stepped with t2d_step_local"};
+        CK(cudaEventRecord(ev0_, stream_));
+        if (!halo_valid_) {   // build the halo of the uploaded particles first (no time step)
+            comm_phase1();
+            comm_phase2();
+        }
+        for (int s = 0; s < nsteps; ++s) {
+            comm_phase1();
+            comm_phase2();
+        }
+        CK(cudaEventRecord(ev1_, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        last_step_ms = ms;
+        CK(cudaGetLastError());
+        return read_fault();
+    }
     if (this->N == 0 || nsteps <= 0) return 0;
     CK(cudaEventRecord(ev0_, stream_));
     for (int s = 0; s < nsteps; ++s) one_step(true, nullptr, nullptr);
@@ -717,6 +982,7 @@ template <typename R> int Engine<R>::step(int nsteps)
 
 template <typename R> int Engine<R>::step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color)
 {
+    if (comm_on_) throw CudaError{"t2d_step_host is not available in slab mode"};
     set_state(N, uv, heading, vid, r3d, nullptr, false);
     int fault = step(1);
     download(uv, heading, vid, r3d, rdot, color, nullptr);
@@ -725,6 +991,7 @@ template <typename R> int Engine<R>::step_host(int N, double* uv, int* heading, 
 
 template <typename R> int Engine<R>::forces(double* F, int* new_heading, int* color)
 {
+    if (comm_on_) throw CudaError{"t2d_forces is not available in slab mode"};
     CK(cudaSetDevice(device_));
     if (this->N == 0) return 0;
     A_.write_F = 1;
@@ -739,7 +1006,7 @@ template <typename R> int Engine<R>::forces(double* F, int* new_heading, int* co
     o.new_heading = (int*)(base + off);
     off += (4 * N + 15) & ~(size_t)15;
     o.color = (int*)(base + off);
-    IoLaunch<R>::egest((int)N, A_.cur, A_.F, A_.new_heading, o, stream_);
+    IoLaunch<R>::egest((int)N, (int)N, nullptr, A_.cur, A_.F, A_.new_heading, o, stream_);
     launches_++;
     if (F) CK(cudaMemcpyAsync(F, o.F, 16 * N, cudaMemcpyDeviceToHost, stream_));
     if (new_heading) CK(cudaMemcpyAsync(new_heading, o.new_heading, 4 * N, cudaMemcpyDeviceToHost, stream_));
@@ -752,15 +1019,15 @@ template <typename R> int Engine<R>::forces(double* F, int* new_heading, int* co
 template <typename R> int Engine<R>::observables(double* out)
 {
     CK(cudaSetDevice(device_));
-    launch_observables(A_.cur.pos, A_.cur.rdot, sizeof(R) == 4, this->N, d_trig_d_.p, d_obs_.p, stream_);
+    launch_observables(A_.cur.pos, A_.cur.rdot, comm_on_ ? A_.cur.aux : nullptr, sizeof(R) == 4, comm_on_ ? capacity_ : this->N,
+                       comm_on_ ? &comm_state_.p->n : nullptr, d_trig_d_.p, d_obs_.p, stream_);
     launches_++;
     double h[T2D_OBS_LEN];
     CK(cudaMemcpyAsync(h, d_obs_.p, sizeof(h), cudaMemcpyDeviceToHost, stream_));
     DevCounters c;
     CK(cudaMemcpyAsync(&c, d_counters_.p, sizeof(c), cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
-    const double n = (double)this->N;
-    h[T2D_OBS_COUNT] = n;
+    const double n = h[T2D_OBS_COUNT];   // owned particles (slab mode skips the halo copies)
     h[T2D_OBS_PHI] = n > 0 ? sqrt(h[T2D_OBS_SUM_COS] * h[T2D_OBS_SUM_COS] + h[T2D_OBS_SUM_SIN] * h[T2D_OBS_SUM_SIN]) / n : 0;
     h[T2D_OBS_MEAN_SPEED] = n > 0 ? h[T2D_OBS_SUM_SPEED] / n : 0;
     h[T2D_OBS_LOST] = (double)c.lost;
@@ -809,6 +1076,7 @@ template <typename R> int Engine<R>::get_r3d(int N, const double* uv, double* r3
     CK(cudaSetDevice(device_));
     StepArgs<R> T = A_;
     T.N = N;
+    T.comm.on = 0;
     T.cur = A_.alt;
     ingest(N, uv, nullptr, nullptr, nullptr, nullptr, T.cur);
     Launch<R>::project_only(T, stream_);
@@ -818,7 +1086,7 @@ template <typename R> int Engine<R>::get_r3d(int N, const double* uv, double* r3
     o.r3d = (double*)base;
     o.vid = (int*)(base + 24 * (size_t)N);
     o.face = (int*)(base + 24 * (size_t)N + ((4 * (size_t)N + 15) & ~(size_t)15));
-    IoLaunch<R>::egest(N, T.cur, A_.F, A_.new_heading, o, stream_);
+    IoLaunch<R>::egest(N, N, nullptr, T.cur, A_.F, A_.new_heading, o, stream_);
     launches_++;
     if (r3d) CK(cudaMemcpyAsync(r3d, o.r3d, 24 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
     if (vid) CK(cudaMemcpyAsync(vid, o.vid, 4 * (size_t)N, cudaMemcpyDeviceToHost, stream_));
@@ -883,6 +1151,7 @@ template <typename R> int Engine<R>::hop_table(uint8_t* out)
 
 template <typename R> int Engine<R>::profile_step(const char** names, double* ms, int cap)
 {
+    if (comm_on_) throw CudaError{"t2d_profile_step is not available in slab mode"};
     CK(cudaSetDevice(device_));
     if (this->N == 0) return 0;
     static const char* kEuclid[] = {"step_fused", "scan", "scatter"};
@@ -1031,6 +1300,63 @@ void t2d_pinned_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
-// multi-GPU entry points live in comm.cu
+// ---- multi-GPU slabs --------------------------------------------------------------------------------------
+int t2d_comm_unique_id(uint8_t id[T2D_UNIQUE_ID_BYTES])
+{
+    std::string err;
+    if (nccl_unique_id(id, &err) != 0) {
+        g_create_error = err;
+        return -1;
+    }
+    return 0;
+}
+int t2d_comm_init(t2d_ctx* ctx, int rank, int world, const uint8_t id[T2D_UNIQUE_ID_BYTES], const double* cuts)
+{
+    if (!id) {
+        ctx->err = "t2d_comm_init needs the NCCL unique id of rank 0 (t2d_comm_unique_id)";
+        return -1;
+    }
+    T2D_TRY(ctx, return ctx->eng->comm_init(rank, world, id, cuts, nullptr, nullptr);)
+}
+int t2d_comm_init_local(t2d_ctx** ctxs, int world, const double* cuts)
+{
+    for (int r = 0; r < world; ++r) {
+        t2d_ctx* c = ctxs[r];
+        T2D_TRY(c, c->eng->comm_init(r, world, nullptr, cuts, r > 0 ? ctxs[r - 1]->eng.get() : nullptr,
+                                     r + 1 < world ? ctxs[r + 1]->eng.get() : nullptr);)
+    }
+    return 0;
+}
+// lockstep drive of a local group: every phase is enqueued for all ranks before the next one, the streams are
+// ordered against each other with events only (no host synchronisation until the end)
+int t2d_step_local(t2d_ctx** ctxs, int world, int32_t nsteps)
+{
+    int fault = 0;
+    try {
+        for (int r = 0; r < world; ++r)
+            if (!ctxs[r]->eng->comm_is_local()) {
+                ctxs[r]->err = "context is not part of a local slab group";
+                return -1;
+            }
+        // the first pass after an upload only builds the halo (no time step); comm_phase2 tracks that per context
+        for (int s = -1; s < nsteps; ++s) {
+            if (s < 0 && ctxs[0]->eng->halo_ready()) continue;
+            for (int r = 0; r < world; ++r) ctxs[r]->eng->comm_phase1();
+            for (int r = 0; r < world; ++r) ctxs[r]->eng->comm_local_send();
+            for (int r = 0; r < world; ++r) ctxs[r]->eng->comm_phase2();
+        }
+        for (int r = 0; r < world; ++r) fault |= ctxs[r]->eng->comm_finish();
+    } catch (const CudaError& e) {
+        ctxs[0]->err = e.msg;
+        return -1;
+    } catch (const std::exception& e) {
+        ctxs[0]->err = e.what();
+        return -1;
+    }
+    return fault;
+}
+int t2d_comm_destroy(t2d_ctx* ctx) { T2D_TRY(ctx, return ctx->eng->comm_destroy();) }
+int32_t t2d_owned_count(t2d_ctx* ctx) { T2D_TRY(ctx, return ctx->eng->owned_count();) }
+int t2d_download_ids(t2d_ctx* ctx, uint32_t* ids) { T2D_TRY(ctx, return ctx->eng->download_ids(ids);) }
 
 }  // extern "C"

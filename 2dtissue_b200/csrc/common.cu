@@ -129,11 +129,15 @@ void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s)
 // observables: sum cos n, sum sin n, sum |rdot| over the resident particles
 // ---------------------------------------------------------------------------------------------------
 template <typename R>
-__global__ void __launch_bounds__(256) k_observables(const Pos3<R>* __restrict__ pos, const Real2<R>* __restrict__ rdot, int N,
+__global__ void __launch_bounds__(256) k_observables(const Pos3<R>* __restrict__ pos, const Real2<R>* __restrict__ rdot,
+                                                     const int4* __restrict__ aux, int N, const int* __restrict__ dN,
                                                      const double2* __restrict__ trig, double* out)
 {
-    double sc = 0, ss = 0, sp = 0;
+    double sc = 0, ss = 0, sp = 0, cnt = 0;
+    if (dN) N = *dN;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        if (aux && aux[i].w < 0) continue;   // halo copy
+        cnt += 1.0;
         int n = (int)pos[i].w;
         double c, s;
         if (n >= TRIG_MIN && n <= TRIG_MAX) {
@@ -150,42 +154,47 @@ __global__ void __launch_bounds__(256) k_observables(const Pos3<R>* __restrict__
         double rx = (double)rdot[i].x, ry = (double)rdot[i].y;
         sp += sqrt(rx * rx + ry * ry);
     }
-    __shared__ double sh[3][8];
+    __shared__ double sh[4][8];
     for (int o = 16; o > 0; o >>= 1) {
         sc += __shfl_down_sync(0xffffffffu, sc, o);
         ss += __shfl_down_sync(0xffffffffu, ss, o);
         sp += __shfl_down_sync(0xffffffffu, sp, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) {
         sh[0][w] = sc;
         sh[1][w] = ss;
         sh[2][w] = sp;
+        sh[3][w] = cnt;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double a = 0, b = 0, c = 0;
+        double a = 0, b = 0, c = 0, d = 0;
         for (int k = 0; k < 8; ++k) {
             a += sh[0][k];
             b += sh[1][k];
             c += sh[2][k];
+            d += sh[3][k];
         }
         atomicAdd(&out[T2D_OBS_SUM_COS], a);
         atomicAdd(&out[T2D_OBS_SUM_SIN], b);
         atomicAdd(&out[T2D_OBS_SUM_SPEED], c);
+        atomicAdd(&out[T2D_OBS_COUNT], d);
     }
 }
 
-void launch_observables(const void* pos, const void* rdot, int is_f32, int N, const double2* trig, double* out8, cudaStream_t s)
+void launch_observables(const void* pos, const void* rdot, const int4* aux, int is_f32, int N, const int* dN,
+                        const double2* trig, double* out8, cudaStream_t s)
 {
     cudaMemsetAsync(out8, 0, sizeof(double) * T2D_OBS_LEN, s);
     if (N <= 0) return;
     int grid = (N + 255) / 256;
     if (grid > 1184) grid = 1184;   // 148 SMs x 8 resident blocks
     if (is_f32)
-        k_observables<float><<<grid, 256, 0, s>>>((const Pos3<float>*)pos, (const Real2<float>*)rdot, N, trig, out8);
+        k_observables<float><<<grid, 256, 0, s>>>((const Pos3<float>*)pos, (const Real2<float>*)rdot, aux, N, dN, trig, out8);
     else
-        k_observables<double><<<grid, 256, 0, s>>>((const Pos3<double>*)pos, (const Real2<double>*)rdot, N, trig, out8);
+        k_observables<double><<<grid, 256, 0, s>>>((const Pos3<double>*)pos, (const Real2<double>*)rdot, aux, N, dN, trig, out8);
 }
 
 }  // namespace t2d

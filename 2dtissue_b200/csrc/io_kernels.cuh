@@ -23,6 +23,7 @@ struct HostViewOut {
     int* face;
     double* F;
     int* new_heading;
+    uint32_t* ids;
 };
 
 template <typename R> __global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleArrays<R> p)
@@ -44,15 +45,20 @@ template <typename R> __global__ void __launch_bounds__(256) k_ingest(int N, Hos
     p.color[i] = 0;
 }
 
-// slot s holds the particle that sits at index aux[s].w of the caller's arrays
+// slot s holds the particle that sits at index aux[s].w of the caller's arrays.  Slab mode (offsets != null): halo
+// copies are skipped and owned particles are written in slot order at their compaction offset.
 template <typename R>
-__global__ void __launch_bounds__(256) k_egest(int N, ParticleArrays<R> p, const Real2<R>* F, const int* new_heading,
-                                               HostViewOut out)
+__global__ void __launch_bounds__(256) k_egest(int resident, int N, const int* __restrict__ offsets, ParticleArrays<R> p,
+                                               const Real2<R>* F, const int* new_heading, HostViewOut out)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= N) return;
+    if (s >= resident) return;
     const int4 ax = p.aux[s];
-    const int o = ax.w;
+    int o = ax.w;
+    if (offsets) {
+        if (ax.w < 0) return;
+        o = offsets[s];
+    }
     if (out.uv) {
         Real2<R> u = p.uv[s];
         out.uv[o] = (double)u.x;
@@ -60,6 +66,7 @@ __global__ void __launch_bounds__(256) k_egest(int N, ParticleArrays<R> p, const
     }
     if (out.vid) out.vid[o] = ax.x;
     if (out.face) out.face[o] = ax.y;
+    if (out.ids) out.ids[o] = (uint32_t)ax.z;
     if (out.r3d || out.heading) {
         Pos3<R> X = p.pos[s];
         if (out.heading) out.heading[o] = (int)X.w;
@@ -81,6 +88,12 @@ __global__ void __launch_bounds__(256) k_egest(int N, ParticleArrays<R> p, const
         out.F[N + o] = (double)f.y;
     }
     if (out.new_heading) out.new_heading[o] = new_heading[s];
+}
+
+template <typename R> __global__ void __launch_bounds__(256) k_owned_flags(int n, ParticleArrays<R> p, int* flags)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) flags[s] = p.aux[s].w >= 0 ? 1 : 0;
 }
 
 template <typename R> __global__ void __launch_bounds__(256) k_in2(int N, const double* src, Real2<R>* dst)
@@ -107,8 +120,9 @@ template <typename R> __global__ void __launch_bounds__(256) k_outN(int N, int c
 
 template <typename R> struct IoLaunch {
     static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s);
-    static void egest(int N, const ParticleArrays<R>& p, const Real2<R>* F, const int* new_heading, const HostViewOut& out,
-                      cudaStream_t s);
+    static void egest(int resident, int N, const int* offsets, const ParticleArrays<R>& p, const Real2<R>* F,
+                      const int* new_heading, const HostViewOut& out, cudaStream_t s);
+    static void owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s);
     static void in2(int N, const double* src, Real2<R>* dst, cudaStream_t s);
     static void out2(int N, const Real2<R>* src, double* dst, cudaStream_t s);
     static void outN(int N, int cols, const R* src, double* dst, cudaStream_t s);
@@ -120,10 +134,14 @@ template <typename R> void IoLaunch<R>::ingest(int N, const HostViewIn& in, cons
     if (N > 0) k_ingest<R><<<(N + 255) / 256, 256, 0, s>>>(N, in, p);
 }
 template <typename R>
-void IoLaunch<R>::egest(int N, const ParticleArrays<R>& p, const Real2<R>* F, const int* new_heading, const HostViewOut& out,
-                        cudaStream_t s)
+void IoLaunch<R>::egest(int resident, int N, const int* offsets, const ParticleArrays<R>& p, const Real2<R>* F,
+                        const int* new_heading, const HostViewOut& out, cudaStream_t s)
 {
-    if (N > 0) k_egest<R><<<(N + 255) / 256, 256, 0, s>>>(N, p, F, new_heading, out);
+    if (resident > 0) k_egest<R><<<(resident + 255) / 256, 256, 0, s>>>(resident, N, offsets, p, F, new_heading, out);
+}
+template <typename R> void IoLaunch<R>::owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s)
+{
+    if (n > 0) k_owned_flags<R><<<(n + 255) / 256, 256, 0, s>>>(n, p, flags);
 }
 template <typename R> void IoLaunch<R>::in2(int N, const double* src, Real2<R>* dst, cudaStream_t s)
 {

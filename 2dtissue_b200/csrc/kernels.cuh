@@ -147,6 +147,12 @@ __device__ __forceinline__ void vox_row_ranges(const StepArgs<R>& a, int x0, int
     }
 }
 
+// number of resident slots: a host constant, or (slab mode) a device-side count that changes every step
+template <typename R> __device__ __forceinline__ int resident_count(const StepArgs<R>& a)
+{
+    return a.comm.on ? a.comm.state->n : a.N;
+}
+
 // bucket key of a particle: nearest-vertex id (table criterion) or compact 3-D cell (Euclidean criterion)
 template <typename R> __device__ __forceinline__ uint32_t bucket_key(const StepArgs<R>& a, const Pos3<R>& X, int vid, BlockCounters& bc)
 {
@@ -239,7 +245,7 @@ template <typename R> __global__ void __launch_bounds__(256) k_bin(StepArgs<R> a
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     BlockCounters bc;
-    if (i < a.N) {
+    if (i < resident_count<R>(a)) {
         uint32_t key = bucket_key<R>(a, a.cur.pos[i], a.cur.aux[i].x, bc);
         a.key[i] = key;
         a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
@@ -253,8 +259,12 @@ template <typename R> __global__ void __launch_bounds__(256) k_bin(StepArgs<R> a
 template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<R> a)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.N) return;
-    const int s = a.start[a.key[i]] + (int)a.rank[i];
+    const int n = a.comm.on ? a.comm.state->n_res : a.N;
+    if (a.comm.on && i == 0) a.comm.state->n = a.start[a.M];   // residents after this sort (nobody reads n in this kernel)
+    if (i >= n) return;
+    const uint32_t key = a.key[i];
+    if (key == KEY_DROP) return;   // slab mode: halo copy of the previous step, or a particle that left
+    const int s = a.start[key] + (int)a.rank[i];
     a.alt.pos[s] = a.cur.pos[i];
     a.alt.uv[s] = a.cur.uv[i];
     a.alt.aux[s] = a.cur.aux[i];
@@ -427,10 +437,13 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
     const int tid = threadIdx.x;
     const int i = blockIdx.x * STEP_THREADS + tid;
     BlockCounters bc;
-    if (i < a.N) {
+    const bool resident = i < resident_count<R>(a);
+    const int4 ai = resident ? a.cur.aux[i] : make_int4(0, 0, 0, ORIGIN_DEAD);
+    if (resident && ai.w < 0) {   // slab mode: halo copies are read by others, never advanced; they leave at the next sort
+        if (MOVING) a.alt.aux[i] = make_int4(0, -1, ai.z, ORIGIN_DEAD);
+    } else if (resident) {
         const Pos3<R> Pi = a.cur.pos[i];
         const Real2<R> ui = a.cur.uv[i];
-        const int4 ai = a.cur.aux[i];
         const int heading = (int)Pi.w;
         int nr = 0;   // non-empty candidate ranges of this particle
         {
@@ -616,9 +629,11 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
             a.alt.aux[i] = make_int4(vid, face, ai.z, ai.w);
             a.alt.rdot[i] = rd;
             a.alt.color[i] = color;
-            const uint32_t key = bucket_key<R>(a, X, vid, bc);
-            a.key[i] = key;
-            a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+            if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
+                const uint32_t key = bucket_key<R>(a, X, vid, bc);
+                a.key[i] = key;
+                a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+            }
         } else {   // t2d_forces: report without moving
             Real2<R> Fv = {fx, fy};
             a.F[i] = Fv;
@@ -849,6 +864,146 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
     flush_counters(bc, a.counters);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// slab mode.  After the step kernel wrote the new state: classify every owned particle by
+// its new 3-D x — stays / migrates to slab-1 or slab+1 — pack migrants (full state) and halo copies (what the
+// neighbour search reads) into the two fixed-capacity messages, and emit key + rank + histogram for what
+// remains resident.  A migrant still within r_max of the cut stays behind as a halo copy, so no second
+// exchange round is needed.
+// ---------------------------------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ CommHeader* msg_header(unsigned char* m) { return reinterpret_cast<CommHeader*>(m); }
+template <typename R> __device__ __forceinline__ MigRec<R>* msg_mig(unsigned char* m) { return reinterpret_cast<MigRec<R>*>(m + 16); }
+template <typename R> __device__ __forceinline__ GhostRec<R>* msg_ghost(unsigned char* m, int mig_cap)
+{
+    return reinterpret_cast<GhostRec<R>*>(m + 16 + (size_t)mig_cap * sizeof(MigRec<R>));
+}
+
+template <typename R> __global__ void __launch_bounds__(256) k_comm_pack(StepArgs<R> a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    BlockCounters bc;
+    const DevComm<R>& cm = a.comm;
+    if (i < cm.state->n) {
+        int4 ax = a.cur.aux[i];
+        uint32_t key = KEY_DROP;
+        if (ax.w >= 0) {
+            const Pos3<R> P = a.cur.pos[i];
+            const R x = P.x;
+            bool keep = true;
+            if (x < cm.lo || x >= cm.hi) {
+                const int dir = x < cm.lo ? 0 : 1;
+                if (x < cm.lo2 || x >= cm.hi2) bc.fault |= T2D_FAULT_MIGRATION;
+                const int slot = atomicAdd(&msg_header<R>(cm.send[dir])->n_mig, 1);
+                if (slot < cm.mig_cap) {
+                    MigRec<R> r;
+                    r.pos = P;
+                    r.uv = a.cur.uv[i];
+                    r.rdot = a.cur.rdot[i];
+                    r.aux = make_int4(ax.x, ax.y, ax.z, 0);
+                    r.color = a.cur.color[i];
+                    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                    msg_mig<R>(cm.send[dir])[slot] = r;
+                } else {
+                    bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+                }
+                keep = dir == 0 ? (x >= cm.lo - cm.halo) : (x < cm.hi + cm.halo);
+                if (keep) {   // still within r_max of the cut: our own particles need it as a neighbour — keep a halo copy
+                    ax.w = ORIGIN_GHOST;
+                    a.cur.aux[i] = ax;
+                }
+            } else {
+#pragma unroll
+                for (int dir = 0; dir < 2; ++dir) {
+                    const bool has = dir == 0 ? cm.rank > 0 : cm.rank < cm.world - 1;
+                    const bool near = dir == 0 ? (x < cm.lo + cm.halo) : (x >= cm.hi - cm.halo);
+                    if (has && near) {
+                        const int slot = atomicAdd(&msg_header<R>(cm.send[dir])->n_ghost, 1);
+                        if (slot < cm.ghost_cap) {
+                            GhostRec<R> g;
+                            g.pos = P;
+                            g.uv = a.cur.uv[i];
+                            g.id = ax.z;
+                            g.pad = 0;
+                            msg_ghost<R>(cm.send[dir], cm.mig_cap)[slot] = g;
+                        } else {
+                            bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+                        }
+                    }
+                }
+            }
+            if (keep) {
+                key = bucket_key<R>(a, P, ax.x, bc);
+                a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+            }
+        }
+        a.key[i] = key;
+    }
+    flush_counters(bc, a.counters);
+}
+
+// append what the two neighbours sent behind the resident slots: migrants become owned particles, halo records
+// become halo copies; each gets key + rank + histogram entry.  One thread per record index and role.
+template <typename R> __global__ void __launch_bounds__(256) k_comm_unpack(StepArgs<R> a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    BlockCounters bc;
+    const DevComm<R>& cm = a.comm;
+    int cnt[4] = {0, 0, 0, 0};   // migrants from rank-1, halo from rank-1, migrants from rank+1, halo from rank+1
+    if (cm.rank > 0) {
+        const CommHeader h = *reinterpret_cast<const CommHeader*>(cm.recv[0]);
+        cnt[0] = min(h.n_mig, cm.mig_cap);
+        cnt[1] = min(h.n_ghost, cm.ghost_cap);
+    }
+    if (cm.rank < cm.world - 1) {
+        const CommHeader h = *reinterpret_cast<const CommHeader*>(cm.recv[1]);
+        cnt[2] = min(h.n_mig, cm.mig_cap);
+        cnt[3] = min(h.n_ghost, cm.ghost_cap);
+    }
+    const int base = cm.state->n;
+    int off[4];
+    off[0] = base;
+    off[1] = off[0] + cnt[0];
+    off[2] = off[1] + cnt[1];
+    off[3] = off[2] + cnt[2];
+    const int total = off[3] + cnt[3];
+    if (t == 0) {
+        cm.state->n_res = min(total, cm.capacity);
+        if (total > cm.capacity) bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+    }
+#pragma unroll
+    for (int role = 0; role < 4; ++role) {
+        if (t >= cnt[role]) continue;
+        const int slot = off[role] + t;
+        if (slot >= cm.capacity) continue;
+        unsigned char* m = const_cast<unsigned char*>(cm.recv[role >> 1]);
+        Pos3<R> P;
+        int vid = 0;
+        if ((role & 1) == 0) {
+            const MigRec<R> r = msg_mig<R>(m)[t];
+            P = r.pos;
+            vid = r.aux.x;
+            a.cur.pos[slot] = r.pos;
+            a.cur.uv[slot] = r.uv;
+            a.cur.rdot[slot] = r.rdot;
+            a.cur.aux[slot] = r.aux;
+            a.cur.color[slot] = r.color;
+        } else {
+            const GhostRec<R> g = msg_ghost<R>(m, cm.mig_cap)[t];
+            P = g.pos;
+            Real2<R> z = {R(0), R(0)};
+            a.cur.pos[slot] = g.pos;
+            a.cur.uv[slot] = g.uv;
+            a.cur.rdot[slot] = z;
+            a.cur.aux[slot] = make_int4(0, -1, g.id, ORIGIN_GHOST);
+            a.cur.color[slot] = 0;
+        }
+        const uint32_t key = bucket_key<R>(a, P, vid, bc);
+        a.key[slot] = key;
+        a.rank[slot] = (uint32_t)atomicAdd(&a.count[key], 1);
+    }
+    flush_counters(bc, a.counters);
+}
+
 // K4+K5 (table mode): seam re-entry, projection, validation (Validation.cpp:40-72), in place, + next key
 template <typename R> __global__ void __launch_bounds__(128) k_wrap_project(StepArgs<R> a)
 {
@@ -943,22 +1098,41 @@ void Launch<R>::voxelize(const DevMesh<R>& m, const double org[3], double cs, do
     if (grid > 148 * 16) grid = 148 * 16;
     k_voxelize<R><<<grid, 256, 0, s>>>(m, org[0], org[1], org[2], cs, reach, nc[0], nc[1], nc[2], nbx, nby, occ);
 }
+// slab mode: the resident count lives on the device and changes every step; grids cover the context's capacity
+template <typename R> static int launch_extent(const StepArgs<R>& a) { return a.comm.on ? a.comm.capacity : a.N; }
+
 template <typename R> void Launch<R>::bin(const StepArgs<R>& a, cudaStream_t s)
 {
-    if (a.N > 0) k_bin<R><<<div_up(a.N, 256), 256, 0, s>>>(a);
+    const int n = launch_extent<R>(a);
+    if (n > 0) k_bin<R><<<div_up(n, 256), 256, 0, s>>>(a);
 }
 template <typename R> void Launch<R>::scatter(const StepArgs<R>& a, cudaStream_t s)
 {
-    if (a.N > 0) k_scatter<R><<<div_up(a.N, 256), 256, 0, s>>>(a);
+    const int n = launch_extent<R>(a);
+    if (n > 0) k_scatter<R><<<div_up(n, 256), 256, 0, s>>>(a);
 }
 template <typename R> void Launch<R>::step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s)
 {
-    if (a.N <= 0) return;
+    const int n = launch_extent<R>(a);
+    if (n <= 0) return;
     constexpr bool EXACT = sizeof(R) == 8;
     if (moving)
-        k_step_euclid<R, EXACT, true><<<div_up(a.N, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
+        k_step_euclid<R, EXACT, true><<<div_up(n, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
     else
-        k_step_euclid<R, EXACT, false><<<div_up(a.N, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
+        k_step_euclid<R, EXACT, false><<<div_up(n, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
+}
+template <typename R> void Launch<R>::comm_pack(const StepArgs<R>& a, cudaStream_t s)
+{
+    k_comm_pack<R><<<div_up(a.comm.capacity, 256), 256, 0, s>>>(a);
+}
+template <typename R> void Launch<R>::comm_unpack(const StepArgs<R>& a, cudaStream_t s)
+{
+    const int n = a.comm.mig_cap > a.comm.ghost_cap ? a.comm.mig_cap : a.comm.ghost_cap;
+    k_comm_unpack<R><<<div_up(n, 256), 256, 0, s>>>(a);
+}
+template <typename R> size_t Launch<R>::comm_message_bytes(int mig_cap, int ghost_cap)
+{
+    return 16 + (size_t)mig_cap * sizeof(MigRec<R>) + (size_t)ghost_cap * sizeof(GhostRec<R>);
 }
 template <typename R> void Launch<R>::neigh_table(const StepArgs<R>& a, cudaStream_t s, int sm_count)
 {

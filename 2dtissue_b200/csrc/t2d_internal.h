@@ -61,6 +61,37 @@ template <typename R> struct ParticleArrays {
     int* color = nullptr;     // neighbour count of the last step (particles_color)
 };
 
+// ---- multi-GPU slabs: message records and the device-side description of one rank's slab ----
+constexpr uint32_t KEY_DROP = 0xffffffffu;   // slot leaves the resident state at the next counting sort
+constexpr int ORIGIN_GHOST = -1;             // aux.w of a halo copy (read by the neighbour search, never updated)
+constexpr int ORIGIN_DEAD = -2;              // aux.w of a slot to be dropped
+
+template <typename R> struct alignas(16) GhostRec {   // what the neighbour search reads of a foreign particle
+    Pos3<R> pos;
+    Real2<R> uv;
+    int id, pad;
+};
+template <typename R> struct alignas(16) MigRec {     // full state of a particle that changes owner
+    Pos3<R> pos;
+    Real2<R> uv, rdot;
+    int4 aux;
+    int color, pad[3];
+};
+struct CommHeader { int n_mig, n_ghost, pad0, pad1; };   // first 16 bytes of every message
+struct DevCommState { int n, n_res; };                   // sorted residents in `cur`; residents after the unpack
+
+template <typename R> struct DevComm {
+    int on = 0;
+    int rank = 0, world = 1;
+    R lo = 0, hi = 0;       // this rank owns x in [lo, hi)
+    R lo2 = 0, hi2 = 0;     // outer boundaries of the two adjacent slabs
+    R halo = 0;             // r_max (+ rounding margin)
+    int mig_cap = 0, ghost_cap = 0, capacity = 0;
+    unsigned char* send[2] = {nullptr, nullptr};         // 0: to rank-1, 1: to rank+1
+    const unsigned char* recv[2] = {nullptr, nullptr};   // 0: from rank-1, 1: from rank+1
+    DevCommState* state = nullptr;
+};
+
 struct DevCounters {   // mirrors t2d_counters' device-updated fields
     unsigned long long pairs_in_range, ties_cutoff, ties_trunc, wraps, wrap_cap_hits, order_fallbacks,
         trig_fallbacks, locate_fallbacks, max_row, lost, nonfinite, cell_fallbacks;
@@ -88,6 +119,7 @@ template <typename R> struct StepArgs {
     DevMesh<R> mesh;
     DevCSR csr;
     DevVox<R> vox;
+    DevComm<R> comm;
     // parameters
     R v0, k, two_sigma, color_r, step_size;
     double eta360;
@@ -108,6 +140,9 @@ template <typename R> struct Launch {
     static void neigh_table(const StepArgs<R>& a, cudaStream_t s, int sm_count);
     static void wrap_project(const StepArgs<R>& a, cudaStream_t s);             // table mode stages 4b-5, in place (+ next keys)
     static void project_only(const StepArgs<R>& a, cudaStream_t s);             // initial projection (get_r3d)
+    static void comm_pack(const StepArgs<R>& a, cudaStream_t s);                // slabs: classify, pack migrants + halo, keys
+    static void comm_unpack(const StepArgs<R>& a, cudaStream_t s);              // slabs: append received particles, keys
+    static size_t comm_message_bytes(int mig_cap, int ghost_cap);
     static void tiling_only(const StepArgs<R>& a, Real2<R>* uv_old, Real2<R>* uv, int* heading, int N, cudaStream_t s);
     static void unit_vectors(const StepArgs<R>& a, const int* heading, R* out, int N, cudaStream_t s);
 };
@@ -115,7 +150,7 @@ template <typename R> struct Launch {
 // precision-independent kernels (common.cu)
 void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s);   // exclusive scan, zeroes count
 int scan_blocks(int M);
-void launch_observables(const void* pos, const void* rdot, int is_f32, int N, const double2* trig, double* out8,
-                        cudaStream_t s);
+void launch_observables(const void* pos, const void* rdot, const int4* aux, int is_f32, int N, const int* dN,
+                        const double2* trig, double* out8, cudaStream_t s);   // aux/dN: slab mode (skip halo copies, device count)
 
 }  // namespace t2d

@@ -12,7 +12,7 @@ from ._lib import Counters, Mesh, Params, Table
 TABLE_NONE, TABLE_DENSE_F64, TABLE_DENSE_F32, TABLE_DENSE_U8, TABLE_HOPS_FROM_MESH = 0, 1, 2, 3, 4
 NEIGH_TABLE, NEIGH_EUCLID = 0, 1
 PRECISION_FP64, PRECISION_FP32 = 0, 1
-FAULT_LOST, FAULT_NONFINITE, FAULT_WRAP_CAP = 1, 2, 4
+FAULT_LOST, FAULT_NONFINITE, FAULT_WRAP_CAP, FAULT_MIGRATION, FAULT_COMM_OVERFLOW = 1, 2, 4, 8, 16
 
 _dp, _ip, _up = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
 
@@ -108,8 +108,23 @@ class Context:
             idp = ids.ctypes.data_as(_up)
         self._chk(self.L.t2d_set_state(self.h, heading.size, _d(uv), _i(heading), _i(vid), _d(r3d), idp), "t2d_set_state")
 
+    # ---- multi-GPU slabs (include/t2d.h "multi-GPU") ----
+    def comm_init(self, rank, world, unique_id, cuts):
+        """NCCL transport, one process per GPU; collective.  unique_id: 128 bytes from comm_unique_id() of rank 0."""
+        cuts = np.ascontiguousarray(cuts, dtype=np.float64)
+        uid = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(self.L.t2d_comm_init(self.h, rank, world, uid, _d(cuts)), "t2d_comm_init")
+
+    def owned_count(self):
+        return self._chk(self.L.t2d_owned_count(self.h), "t2d_owned_count")
+
+    def download_ids(self):
+        ids = np.zeros(self.owned_count(), dtype=np.uint32)
+        self._chk(self.L.t2d_download_ids(self.h, ids.ctypes.data_as(_up)), "t2d_download_ids")
+        return ids
+
     def download(self, fields=("uv", "n", "vid", "r3d", "rdot", "color", "face")):
-        N = self.N
+        N = self.owned_count()
         out = {}
         if "uv" in fields:
             out["uv"] = np.zeros(2 * N)
@@ -200,6 +215,99 @@ class Context:
         ms = np.zeros(16)
         n = self._chk(self.L.t2d_profile_step(self.h, names, _d(ms), 16), "t2d_profile_step")
         return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and broadcasts it, e.g. with torch.distributed)."""
+    L = _lib.load()
+    buf = (C.c_ubyte * 128)()
+    if L.t2d_comm_unique_id(buf) != 0:
+        raise T2DError("t2d_comm_unique_id failed: %s" % L.t2d_last_error(None).decode())
+    return bytes(buf)
+
+
+def slab_cuts(x, world):
+    """world-1 interior slab boundaries along x with equal particle counts (cuts chosen so that
+    particle counts are equal at t = 0).  A cut is placed midway between two consecutive sorted x values."""
+    x = np.sort(np.asarray(x, dtype=np.float64))
+    cuts = []
+    for r in range(1, world):
+        k = (len(x) * r) // world
+        cuts.append(0.5 * (x[k - 1] + x[k]) if 0 < k < len(x) else (x[-1] if len(x) else 0.0))
+    return np.array(cuts, dtype=np.float64)
+
+
+def slab_of(x, cuts):
+    """Owner rank of every particle: slab r owns x in [cuts[r-1], cuts[r])."""
+    return np.searchsorted(np.asarray(cuts, dtype=np.float64), np.asarray(x, dtype=np.float64), side="right").astype(np.int32)
+
+
+def partition_by_slab(state, cuts, rank):
+    """The sub-state (with global ids) that `rank` owns.  state: dict(uv, n, vid, r3d) in the reference's layouts."""
+    N = state["n"].size
+    x = state["r3d"][:N]
+    sel = np.nonzero(slab_of(x, cuts) == rank)[0]
+    col = lambda a, k: np.concatenate([a[j * N:(j + 1) * N][sel] for j in range(k)])
+    return dict(uv=col(state["uv"], 2), n=state["n"][sel], vid=state["vid"][sel], r3d=col(state["r3d"], 3),
+                ids=sel.astype(np.uint32))
+
+
+def merge_by_id(parts, N):
+    """Inverse of partition_by_slab for downloaded per-rank results: dict of arrays in global-id order."""
+    out = {}
+    for p in parts:
+        ids = p["ids"].astype(np.int64)
+        m = ids.size
+        for k, a in p.items():
+            if k == "ids":
+                continue
+            cols = a.size // m if m else 1
+            if k not in out:
+                cols = {"uv": 2, "rdot": 2, "r3d": 3}.get(k, 1)
+                out[k] = np.zeros(cols * N, dtype=a.dtype)
+            cols = out[k].size // N
+            for j in range(cols):
+                out[k][j * N + ids] = a[j * m:(j + 1) * m]
+    return out
+
+
+class LocalSlabGroup:
+    """`world` contexts driven by one host thread (t2d_comm_init_local / t2d_step_local): P logical slabs on one GPU
+    (parity tests: P slabs == 1 GPU) or one context per GPU of a box."""
+
+    def __init__(self, chart, world, cuts, devices=None, **ctx_kw):
+        self.world, self.cuts = world, np.ascontiguousarray(cuts, dtype=np.float64)
+        devices = devices or [0] * world
+        self.ctxs = [Context(chart, device=devices[r], **ctx_kw) for r in range(world)]
+        self.L = self.ctxs[0].L
+        self._arr = (C.c_void_p * world)(*[c.h for c in self.ctxs])
+        if self.L.t2d_comm_init_local(self._arr, world, _d(self.cuts)) != 0:
+            raise T2DError("t2d_comm_init_local failed: %s" % self.L.t2d_last_error(self.ctxs[0].h).decode())
+        self.N = 0
+
+    def set_state(self, state):
+        self.N = state["n"].size
+        for r, c in enumerate(self.ctxs):
+            p = partition_by_slab(state, self.cuts, r)
+            c.set_state(p["uv"], p["n"], p["vid"], p["r3d"], ids=p["ids"])
+
+    def step(self, nsteps=1):
+        rc = self.L.t2d_step_local(self._arr, self.world, nsteps)
+        if rc < 0:
+            raise T2DError("t2d_step_local failed: %s" % self.L.t2d_last_error(self.ctxs[0].h).decode())
+        return rc
+
+    def download(self, fields=("uv", "n", "vid", "r3d", "rdot", "color", "face")):
+        parts = []
+        for c in self.ctxs:
+            d = c.download(fields)
+            d["ids"] = c.download_ids()
+            parts.append(d)
+        return merge_by_id(parts, self.N), [p["ids"].size for p in parts]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
 
 
 def seed_particles(N, seed=1234, first_id=0):

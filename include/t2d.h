@@ -58,7 +58,11 @@ typedef struct {
 
 enum { T2D_NEIGH_TABLE = 0, T2D_NEIGH_EUCLID = 1 };
 enum { T2D_PRECISION_FP64 = 0, T2D_PRECISION_FP32 = 1 };
-enum { T2D_FAULT_LOST = 1, T2D_FAULT_NONFINITE = 2, T2D_FAULT_WRAP_CAP = 4 };
+enum {
+    T2D_FAULT_LOST = 1, T2D_FAULT_NONFINITE = 2, T2D_FAULT_WRAP_CAP = 4,
+    T2D_FAULT_MIGRATION = 8,      /* multi-GPU: a particle moved beyond the adjacent slab in one step */
+    T2D_FAULT_COMM_OVERFLOW = 16  /* multi-GPU: a halo/migration message or the context's capacity overflowed */
+};
 
 /* _2DTissue ctor arguments that reach the step (2DTissue.h:37-54) + the extensions of SURVEY.md App. A */
 typedef struct {
@@ -167,12 +171,29 @@ int t2d_profile_step(t2d_ctx* ctx, const char** names, double* ms, int cap);
 void* t2d_pinned_alloc(size_t bytes);
 void t2d_pinned_free(void* p);
 
-/* ---- multi-GPU: one context per rank, spatial slabs along x, NCCL halo + migration -- */
+/* ---- multi-GPU: one context per rank, spatial slabs along the 3-D x axis ----------------
+ * Euclidean criterion only.  Rank r owns the particles whose 3-D x lies in [cuts[r-1], cuts[r]) (cuts[-1] = -inf,
+ * cuts[world-1] = +inf); mesh, cos/sin tables and the cell index are replicated.  Once per step every rank sends
+ * to slab r-1 and r+1 (a) the particles that migrated there (full state) and (b) copies of its particles within
+ * r_max of the cut (halo: position, heading, uv, id), in ONE fixed-capacity message per direction; counts travel in
+ * the message header, so the host never synchronises inside t2d_step.  Global ids travel with the particles: the
+ * summation order and the (seed, step, id) noise are partition independent, results equal the single-GPU ones.
+ * After t2d_comm_init*, t2d_set_state/t2d_set_particles take ONLY the particles this rank owns (with their global
+ * ids); t2d_download returns the currently owned particles in device order, t2d_download_ids their global ids,
+ * t2d_owned_count how many there are.  capacity must leave room for halo copies and migration imbalance. */
 #define T2D_UNIQUE_ID_BYTES 128
 int t2d_comm_unique_id(uint8_t id[T2D_UNIQUE_ID_BYTES]);
-/* cuts[world+1]: ascending slab boundaries along x (cuts[0] = -inf, cuts[world] = +inf are implied) */
+/* one process per GPU, NCCL transport (ncclSend/ncclRecv to rank-1 and rank+1 inside one group).
+ * cuts: world-1 ascending interior boundaries.  Collective: every rank of the communicator must call it. */
 int t2d_comm_init(t2d_ctx* ctx, int rank, int world, const uint8_t id[T2D_UNIQUE_ID_BYTES], const double* cuts);
+/* one process driving `world` contexts (on the same or on different GPUs): the exchange is a device-to-device
+ * copy into the neighbour context's receive buffer.  Lets P logical slabs run on ONE GPU (parity tests) or one
+ * host thread drive a whole box.  Step the group with t2d_step_local, not t2d_step. */
+int t2d_comm_init_local(t2d_ctx** ctxs, int world, const double* cuts);
+int t2d_step_local(t2d_ctx** ctxs, int world, int32_t nsteps);   /* returns the OR of all ranks' fault masks */
 int t2d_comm_destroy(t2d_ctx* ctx);
+int32_t t2d_owned_count(t2d_ctx* ctx);                  /* synchronises; also refreshes t2d_particle_count */
+int t2d_download_ids(t2d_ctx* ctx, uint32_t* ids);      /* global ids in the order t2d_download uses */
 
 #ifdef __cplusplus
 }
