@@ -193,6 +193,12 @@ template <typename R> class Engine : public EngineBase {
     DevBuf<int> d_cflag_, d_coff_, d_cblk_;
     cudaEvent_t ev_sent_ = nullptr, ev_consumed_ = nullptr;
     std::vector<double> cuts_;
+    cudaEvent_t* prof_ev_ = nullptr;   // t2d_profile_step in slab mode: events between the kernels of one step
+    int* prof_nev_ = nullptr;
+    void prof_mark()
+    {
+        if (prof_ev_) cudaEventRecord(prof_ev_[(*prof_nev_)++], stream_);
+    }
     double vox_sigma_ = -1, vox_color_ = -1;
     int64_t launches_ = 0, steps_ = 0;
 
@@ -785,8 +791,10 @@ int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* c
     A_.comm.halo = (R)(rmax * (1.0 + (sizeof(R) == 8 ? 1e-9 : 1e-3)));
     if (world > 1 && (double)A_.comm.hi - (double)A_.comm.lo < 4.0 * rmax && rank > 0 && rank < world - 1)
         throw CudaError{"slab narrower than 4 r_max"};
-    A_.comm.mig_cap = std::max(1024, capacity_ / 64);
-    A_.comm.ghost_cap = std::max(4096, capacity_ / 16);
+    // fixed message capacity per direction: migrants are ~0.1 % of a slab per step, the halo strip ~1 % at 2 M
+    // particles per GPU (both measured); T2D_FAULT_COMM_OVERFLOW reports a message that did not fit
+    A_.comm.mig_cap = std::max(2048, capacity_ / 256);
+    A_.comm.ghost_cap = std::max(8192, capacity_ / 32);
     A_.comm.capacity = capacity_;
     msg_bytes_ = Launch<R>::comm_message_bytes(A_.comm.mig_cap, A_.comm.ghost_cap);
     for (int d = 0; d < 2; ++d) {
@@ -841,14 +849,17 @@ template <typename R> void Engine<R>::comm_phase1()
 {
     CK(cudaSetDevice(device_));
     for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(comm_send_[d].p, 0, 16, stream_));
+    prof_mark();
     if (halo_valid_) {
         A_.step = (uint64_t)step_index;
         Launch<R>::step_euclid(A_, true, stream_);   // cur -> alt
         std::swap(A_.cur, A_.alt);
         launches_++;
     }
+    prof_mark();
     Launch<R>::comm_pack(A_, stream_);
     launches_++;
+    prof_mark();
 }
 
 template <typename R> void Engine<R>::comm_local_send()
@@ -875,10 +886,13 @@ template <typename R> void Engine<R>::comm_phase2()
             if (peer_[d]) CK(cudaStreamWaitEvent(stream_, peer_[d]->comm_event(0), 0));
     }
     Launch<R>::comm_unpack(A_, stream_);
+    prof_mark();
     launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
+    prof_mark();
     Launch<R>::scatter(A_, stream_);
     std::swap(A_.cur, A_.alt);
     launches_ += 5;
+    prof_mark();
     CK(cudaEventRecord(ev_consumed_, stream_));
     if (halo_valid_) {
         step_index++;
@@ -1151,8 +1165,32 @@ template <typename R> int Engine<R>::hop_table(uint8_t* out)
 
 template <typename R> int Engine<R>::profile_step(const char** names, double* ms, int cap)
 {
-    if (comm_on_) throw CudaError{"t2d_profile_step is not available in slab mode"};
     CK(cudaSetDevice(device_));
+    if (comm_on_) {   // collective in NCCL mode: every rank must call it
+        if (!link_) throw CudaError{"t2d_profile_step: local slab groups are not supported"};
+        static const char* kSlab[] = {"step_fused", "comm_pack", "exchange_unpack", "scan", "scatter"};
+        if (!halo_valid_) step(0);
+        cudaEvent_t ev[8];
+        for (auto& e : ev) CK(cudaEventCreate(&e));
+        int nev = 0;
+        prof_ev_ = ev;
+        prof_nev_ = &nev;
+        comm_phase1();
+        comm_phase2();
+        prof_ev_ = nullptr;
+        prof_nev_ = nullptr;
+        CK(cudaStreamSynchronize(stream_));
+        int n = std::min(cap, nev - 1);
+        for (int i = 0; i < n; ++i) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            names[i] = kSlab[i];
+            ms[i] = t;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        read_fault();
+        return n;
+    }
     if (this->N == 0) return 0;
     static const char* kEuclid[] = {"step_fused", "scan", "scatter"};
     static const char* kTable[] = {"neigh_table", "wrap_project", "scan", "scatter"};

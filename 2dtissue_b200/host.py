@@ -123,6 +123,22 @@ class Context:
         self._chk(self.L.t2d_download_ids(self.h, ids.ctypes.data_as(_up)), "t2d_download_ids")
         return ids
 
+    def download_into(self, bufs):
+        """Download into caller-provided (e.g. pinned) arrays sized for the context's capacity; returns N owned.
+        bufs: dict with any of uv, n, vid, r3d, rdot, color, face, ids.  Layout = the reference's, with stride N."""
+        N = self.owned_count()
+        g = bufs.get
+        self._chk(self.L.t2d_download(self.h, _d(g("uv")), _i(g("n")), _i(g("vid")), _d(g("r3d")), _d(g("rdot")),
+                                      _i(g("color")), _i(g("face"))), "t2d_download")
+        if g("ids") is not None:
+            self._chk(self.L.t2d_download_ids(self.h, g("ids").ctypes.data_as(_up)), "t2d_download_ids")
+        return N
+
+    def set_state_raw(self, N, uv, heading, vid, r3d, ids=None):
+        """set_state without any host-side copy: arrays may be larger than needed (first 2N / N / 3N entries are used)."""
+        self._chk(self.L.t2d_set_state(self.h, N, _d(uv), _i(heading), _i(vid), _d(r3d),
+                                       ids.ctypes.data_as(_up) if ids is not None else None), "t2d_set_state")
+
     def download(self, fields=("uv", "n", "vid", "r3d", "rdot", "color", "face")):
         N = self.owned_count()
         out = {}

@@ -34,8 +34,8 @@ B_ALG = {("f32", "table"): 144, ("f32", "euclid"): 192, ("f64", "table"): 208, (
 # Euclid kernel is credited with the stages it replaces (K3 + K4/K5), the counting-sort scatter with K1 + K2;
 # no credit is taken for the traffic the fusion saves.
 B_KERNEL = {
-    ("f32", "euclid"): {"step_fused": (24 + 16) + 68, "scan": 0, "scatter": 16 + (36 + 16)},
-    ("f64", "euclid"): {"step_fused": (36 + 24) + 104, "scan": 0, "scatter": 16 + (52 + 32)},
+    ("f32", "euclid"): {"step_fused": (24 + 16) + 68, "scan": 0, "scatter": 16 + (36 + 16), "comm_pack": 0, "exchange_unpack": 0},
+    ("f64", "euclid"): {"step_fused": (36 + 24) + 104, "scan": 0, "scatter": 16 + (52 + 32), "comm_pack": 0, "exchange_unpack": 0},
     ("f32", "table"): {"neigh_table": 24, "wrap_project": 68, "scan": 0, "scatter": 16 + 36},
     ("f64", "table"): {"neigh_table": 36, "wrap_project": 104, "scan": 0, "scatter": 16 + 52},
 }
@@ -202,12 +202,39 @@ def main_ours(args, rank, world, local_rank):
     prec = t2d.PRECISION_FP32 if spec["dtype"] == "f32" else t2d.PRECISION_FP64
     Nloc = spec["per_gpu"]
     sigma = sigma_for(spec["total"]) if mode == t2d.NEIGH_EUCLID else 0.4166666666666667
-    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=Nloc, device=local_rank)
+    slabs = world > 1
+    if slabs and mode != t2d.NEIGH_EUCLID:
+        raise SystemExit("multi-GPU slabs support the Euclidean criterion (workloads c4shard / c2)")
+    cap = int(Nloc * 1.25) + 65536 if slabs else Nloc      # room for halo copies and migration imbalance
+    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=cap, device=local_rank)
     if mode == t2d.NEIGH_TABLE:
         kw["table_kind"] = t2d.TABLE_HOPS_FROM_MESH
     ctx = t2d.Context(chart, **kw)
-    uv, n = t2d.seed_particles(Nloc, seed=1234 + rank)
-    ctx.set_particles(uv, n, ids=(np.arange(Nloc, dtype=np.uint32) + np.uint32(rank * Nloc)) if world > 1 else None)
+    if not slabs:
+        uv, n = t2d.seed_particles(Nloc, seed=1234)
+        ctx.set_particles(uv, n)
+    else:
+        # ONE global particle set (spec["total"]), seeded identically on every rank; every rank projects it on its own
+        # GPU (deterministic), so equal-count slab cuts along x agree everywhere without communication; each rank then
+        # uploads only the slab it owns, with global ids
+        Ntot = spec["total"]
+        uv, n = t2d.seed_particles(Ntot, seed=1234)
+        r3d, vid = np.zeros(3 * Ntot), np.zeros(Ntot, dtype=np.int32)
+        for a in range(0, Ntot, cap):
+            b = min(Ntot, a + cap)
+            rr, vv, _ = ctx.get_r3d(np.concatenate([uv[a:b], uv[Ntot + a:Ntot + b]]))
+            m = b - a
+            for k in range(3):
+                r3d[k * Ntot + a:k * Ntot + b] = rr[k * m:(k + 1) * m]
+            vid[a:b] = vv
+        cuts = t2d.slab_cuts(r3d[:Ntot], world)
+        uid = [t2d.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0], cuts)
+        part = t2d.partition_by_slab(dict(uv=uv, n=n, vid=vid, r3d=r3d), cuts, rank)
+        ctx.set_state(part["uv"], part["n"], part["vid"], part["r3d"], ids=part["ids"])
+        del uv, n, r3d, vid
+        ctx.step(0)                                        # builds the halo (collective), no time step
 
     def barrier():
         if dist is not None:
@@ -249,25 +276,47 @@ def main_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.destroy_process_group()
         return
-    # end-to-end through the drop-in call with pinned host buffers
+    # end-to-end through the public call with pinned HOST buffers in the reference's layouts: single GPU = the
+    # literal drop-in t2d_step_host (upload -> step -> download); slabs = upload of the owned slab + step + download
     e2e_steps = max(2, min(args.steps, 10))
-    s = ctx.download(("uv", "n", "vid", "r3d"))
     pin = lambda a: torch.from_numpy(a.copy()).pin_memory().numpy()
-    h_uv, h_n, h_vid, h_r3d = pin(s["uv"]), pin(s["n"]), pin(s["vid"]), pin(s["r3d"])
-    h_rdot, h_col = pin(np.zeros(2 * Nloc)), pin(np.zeros(Nloc, dtype=np.int32))
-    ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col)
-    barrier()
-    te = time.perf_counter()
-    for _ in range(e2e_steps):
+    if not slabs:
+        s = ctx.download(("uv", "n", "vid", "r3d"))
+        h_uv, h_n, h_vid, h_r3d = pin(s["uv"]), pin(s["n"]), pin(s["vid"]), pin(s["r3d"])
+        h_rdot, h_col = pin(np.zeros(2 * Nloc)), pin(np.zeros(Nloc, dtype=np.int32))
         ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col)
-    barrier()
-    e2e_s = time.perf_counter() - te
+        barrier()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col)
+        barrier()
+        e2e_s = time.perf_counter() - te
+        h2d = Nloc * (16 + 4 + 4 + 24)
+        d2h = Nloc * (16 + 4 + 4 + 24 + 16 + 4)
+    else:
+        pinz = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
+        hb = dict(uv=pinz(2 * cap, torch.float64), n=pinz(cap, torch.int32), vid=pinz(cap, torch.int32),
+                  r3d=pinz(3 * cap, torch.float64), rdot=pinz(2 * cap, torch.float64), color=pinz(cap, torch.int32),
+                  ids=pinz(cap, torch.int32).view(np.uint32))
+        No = ctx.download_into(hb)
+        h2d = d2h = 0
+        barrier()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.set_state_raw(No, hb["uv"], hb["n"], hb["vid"], hb["r3d"], hb["ids"])
+            ctx.step(1)
+            h2d += No * (16 + 4 + 4 + 24 + 4)
+            No = ctx.download_into(hb)
+            d2h += No * (16 + 4 + 4 + 24 + 16 + 4 + 4)
+        barrier()
+        e2e_s = time.perf_counter() - te
+        tb = torch.tensor([h2d / e2e_steps, d2h / e2e_steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tb)
+        h2d, d2h = float(tb[0].item()) / world, float(tb[1].item()) / world   # per-rank means; scaled by world below
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = spec["total"] * e2e_steps / float(t.item())
-    h2d = Nloc * (16 + 4 + 4 + 24)
-    d2h = Nloc * (16 + 4 + 4 + 24 + 16 + 4)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -289,7 +338,9 @@ def main_ours(args, rank, world, local_rank):
                 "config": {"workload": spec["name"], "particles_total": spec["total"], "sigma": sigma,
                            "mesh_V": int(len(chart["uv"])), "mesh_F": int(len(chart["faces"])),
                            "l2": "per-step working set (%d MB) exceeds the 126 MB L2; no explicit flush" %
-                                 int(Nloc * 112 / 1e6 + 32), "parallelism": "slab%d" % world if world > 1 else "single",
+                                 int(Nloc * 112 / 1e6 + 32),
+                           "parallelism": ("slab%d: x-slabs of one %d-particle set, NCCL halo + migration exchange per step" %
+                                           (world, spec["total"])) if world > 1 else "single",
                            "fault": fault},
                 "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                 "kernel_ms": prof, "roofline": roof,
