@@ -41,6 +41,15 @@ B_KERNEL = {
 }
 
 
+def measured_traffic(workload, dtype, kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t["%s/%s/%s" % (workload, dtype, kernel)]["bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -327,7 +336,8 @@ def main_ours(args, rank, world, local_rank):
             bk = B_KERNEL[key][dom]
             ach = bk * Nloc / (prof[dom] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel_ms": prof[dom], "alg_bytes_per_particle": bk,
+                    "traffic": measured_traffic(args.workload, spec["dtype"], dom) if world == 1 and not args.particles_per_gpu else None,
+                    "peak_source": peak_src, "kernel_ms": prof[dom], "alg_bytes_per_particle": bk,
                     "step_alg_bytes_per_particle": B_ALG[key],
                     "step_achieved_gbs": B_ALG[key] * Nloc / (ms_per_step * 1e-3) / 1e9,
                     "step_frac": B_ALG[key] * Nloc / (ms_per_step * 1e-3) / 1e9 / peak}

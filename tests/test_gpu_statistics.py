@@ -1,0 +1,57 @@
+"""Long runs are chaotic, so the fp32 fast path is compared with the reference semantics STATISTICALLY
+(BASELINE.json north_star): polar order parameter and mean speed, mean over seeds within 3 standard errors.
+The fp64 path needs no such test — it is bit-identical to the oracle step by step (test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _series_gpu(t2d, chart, uv, n, sigma, eta, seed, steps, precision):
+    N = n.size
+    ctx = t2d.Context(chart, v0=0.1, k=1.0, sigma=sigma, step_size=0.001, eta=eta, seed=seed, neigh_mode=t2d.NEIGH_EUCLID,
+                      precision=precision, capacity=N)
+    ctx.set_particles(uv, n)
+    phi, spd = [], []
+    for _ in range(steps):
+        assert ctx.step(1) == 0
+        o = ctx.observables()
+        phi.append(o["phi"])
+        spd.append(o["mean_speed"])
+    ctx.close()
+    return np.array(phi), np.array(spd)
+
+
+def _series_oracle(oracle, t2d, chart, uv, n, sigma, eta, seed, steps):
+    r3d, vid, _ = oracle.get_r3d(uv)
+    st = dict(uv=uv, n=n, vid=vid, r3d=r3d)
+    phi, spd = [], []
+    for s in range(steps):
+        st = oracle.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, eta=eta, seed=seed, mode=1,
+                         step_index=s, threads=0)
+        assert st["fault"] == 0
+        p, v = oracle.observables(st["n"], st["rdot"])
+        phi.append(p)
+        spd.append(v)
+    return np.array(phi), np.array(spd)
+
+
+def test_fp32_long_run_statistics_match_reference_semantics(t2d, chart, oracle):
+    N, steps, eta, nseeds = 3000, 150, 0.1, 6
+    sigma = float(np.sqrt(0.5 * 451.3 / (np.pi * N)))
+    tail = slice(steps // 2, steps)
+    g_phi, g_spd, o_phi, o_spd = [], [], [], []
+    for s in range(nseeds):
+        uv, n = t2d.seed_particles(N, seed=500 + s)
+        a, b = _series_gpu(t2d, chart, uv, n, sigma, eta, 1000 + s, steps, t2d.PRECISION_FP32)
+        c, d = _series_oracle(oracle, t2d, chart, uv, n, sigma, eta, 1000 + s, steps)
+        # the first step is still deterministic to fp32 accuracy
+        assert abs(a[0] - c[0]) < 5e-3 and abs(b[0] - d[0]) < 1e-3 * max(1.0, d[0])
+        g_phi.append(a[tail].mean()); g_spd.append(b[tail].mean())
+        o_phi.append(c[tail].mean()); o_spd.append(d[tail].mean())
+    for name, g, o in (("phi", np.array(g_phi), np.array(o_phi)), ("mean speed", np.array(g_spd), np.array(o_spd))):
+        se = np.sqrt(g.var(ddof=1) / nseeds + o.var(ddof=1) / nseeds)
+        print("%s: fp32 %.5f +- %.5f | oracle %.5f +- %.5f | diff %.2e, 3 s.e. %.2e" %
+              (name, g.mean(), g.std(ddof=1) / np.sqrt(nseeds), o.mean(), o.std(ddof=1) / np.sqrt(nseeds),
+               abs(g.mean() - o.mean()), 3 * se))
+        assert abs(g.mean() - o.mean()) <= 3 * se + 1e-4 * max(1.0, abs(o.mean()))
