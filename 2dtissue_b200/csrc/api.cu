@@ -209,7 +209,7 @@ template <typename R> class Engine : public EngineBase {
     DevBuf<int> d_gstart_, d_gfaces_;
     DevBuf<double2> d_trig_d_;
     DevBuf<CrEntry> d_cr_;
-    DevBuf<uint4> d_vox_blocks_;
+    DevBuf<uint2> d_vox_words_;
     DevBuf<int> d_csr_start_, d_csr_col_;
     DevBuf<double> d_csr_d_;
     DevBuf<int> d_adj_start_, d_adj_;
@@ -218,6 +218,7 @@ template <typename R> class Engine : public EngineBase {
     DevBuf<Pos3<R>> d_pos_[2];
     DevBuf<int4> d_aux_[2];
     DevBuf<int> d_color_[2], d_new_heading_;
+    DevBuf<double2> d_cs_[2];
     DevBuf<uint32_t> d_key_, d_rank_;
     DevBuf<int> d_count_, d_start_, d_blocksums_, d_work_;
     DevBuf<DevCounters> d_counters_;
@@ -282,6 +283,7 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
         d_aux_[b].alloc(C);
         d_rdot_[b].alloc(C);
         d_color_[b].alloc(C);
+        if (sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID) d_cs_[b].alloc(C);
     }
     d_uv_new_.alloc(C);
     d_F_.alloc(C);
@@ -295,8 +297,8 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     d_stage_in_.alloc(C * (16 + 4 + 4 + 24 + 4) + 256);
     d_stage_out_.alloc(C * (16 + 4 + 4 + 24 + 16 + 4 + 4 + 16 + 4) + 256);
 
-    A_.cur = {d_pos_[0].p, d_uv_[0].p, d_aux_[0].p, d_rdot_[0].p, d_color_[0].p};
-    A_.alt = {d_pos_[1].p, d_uv_[1].p, d_aux_[1].p, d_rdot_[1].p, d_color_[1].p};
+    A_.cur = {d_pos_[0].p, d_uv_[0].p, d_aux_[0].p, d_rdot_[0].p, d_color_[0].p, d_cs_[0].p};
+    A_.alt = {d_pos_[1].p, d_uv_[1].p, d_aux_[1].p, d_rdot_[1].p, d_color_[1].p, d_cs_[1].p};
     A_.key = d_key_.p;
     A_.rank = d_rank_.p;
     A_.uv_new = d_uv_new_.p;
@@ -491,9 +493,10 @@ template <typename R> void Engine<R>::alloc_buckets(int nbuckets)
     A_.blocksums = d_blocksums_.p;
 }
 
-// Sparse voxel index of the 3-D cell list (t2d_internal.h DevVox).  Cell edge = 2*rmax*(1+margin); the cells a
+// Sparse row index of the 3-D cell list (t2d_internal.h DevVox).  Cell edge = 2*rmax*(1+margin); the cells a
 // particle can ever occupy are those the mesh surface touches (positions are convex combinations of a face's
-// corners, CellHelper.cpp:143-146), found by a GPU voxelisation; blocks are numbered along a Morton curve.
+// corners, CellHelper.cpp:143-146), found by a GPU voxelisation.  Compact indices ascend along x inside a row; the
+// rows follow a Morton curve over (y, z) (T2D_ROW_ORDER=lex: plain (z, y) order, for A/B measurements).
 template <typename R> void Engine<R>::build_vox()
 {
     const double two_sigma = 2 * P_.sigma, color_r = P_.color_factor * P_.sigma;
@@ -508,66 +511,70 @@ template <typename R> void Engine<R>::build_vox()
             mx[k] = std::max(mx[k], chart_.x3d[3 * (size_t)v + k]);
         }
     double org[3];
-    int nc[3], nb[3];
+    int nc[3];
     double extent = 0;
     for (int k = 0; k < 3; ++k) {
         org[k] = mn[k] - 2.0 * cs;
         double n = std::floor((mx[k] - org[k]) / cs) + 3.0;
         if (n > 2.0e9) throw CudaError{"sigma is too small for the mesh extent (cell grid axis overflows)"};
         nc[k] = (int)n;
-        nb[k] = (nc[k] + 3) / 4;
         extent = std::max(extent, mx[k] - mn[k]);
     }
-    const double nblocks_d = (double)nb[0] * nb[1] * nb[2];
-    if (nblocks_d > 4.0e8) throw CudaError{"sigma is too small for the mesh extent (the block table of the cell list would exceed 6 GB)"};
-    const size_t nblocks = (size_t)nblocks_d;
+    const int nwx = (nc[0] + 31) / 32;
+    const size_t nrows = (size_t)nc[1] * nc[2];
+    const double nwords_d = (double)nrows * nwx;
+    if (nwords_d > 7.5e8) throw CudaError{"sigma is too small for the mesh extent (the row table of the cell list would exceed 6 GB)"};
+    const size_t nwords = (size_t)nwords_d;
     const double reach = 0.5 * std::sqrt(3.0) * cs + 0.02 * cs + 2e-5 * extent;
 
-    DevBuf<unsigned long long> d_occ;
-    d_occ.alloc(nblocks);
-    CK(cudaMemsetAsync(d_occ.p, 0, nblocks * sizeof(unsigned long long), stream_));
-    Launch<R>::voxelize(A_.mesh, org, cs, reach, nc, nb[0], nb[1], d_occ.p, stream_);
+    DevBuf<unsigned> d_occ;
+    d_occ.alloc(nwords);
+    CK(cudaMemsetAsync(d_occ.p, 0, nwords * sizeof(unsigned), stream_));
+    Launch<R>::voxelize(A_.mesh, org, cs, reach, nc, nwx, d_occ.p, stream_);
     launches_++;
-    std::vector<unsigned long long> occ(nblocks);
-    CK(cudaMemcpyAsync(occ.data(), d_occ.p, nblocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    std::vector<unsigned> occ(nwords);
+    CK(cudaMemcpyAsync(occ.data(), d_occ.p, nwords * sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     CK(cudaGetLastError());
 
-    // occupied blocks in Morton order -> compact base index
-    auto spread = [](uint64_t v) {   // 21 bits -> every third bit
-        v &= 0x1fffffull;
-        v = (v | v << 32) & 0x1f00000000ffffull;
-        v = (v | v << 16) & 0x1f0000ff0000ffull;
-        v = (v | v << 8) & 0x100f00f00f00f00full;
-        v = (v | v << 4) & 0x10c30c30c30c30c3ull;
-        v = (v | v << 2) & 0x1249249249249249ull;
+    // non-empty rows in Morton order over (y, z) -> compact base index of every word
+    auto spread = [](uint64_t v) {   // 32 bits -> every second bit
+        v &= 0xffffffffull;
+        v = (v | v << 16) & 0x0000ffff0000ffffull;
+        v = (v | v << 8) & 0x00ff00ff00ff00ffull;
+        v = (v | v << 4) & 0x0f0f0f0f0f0f0f0full;
+        v = (v | v << 2) & 0x3333333333333333ull;
+        v = (v | v << 1) & 0x5555555555555555ull;
         return v;
     };
+    const char* ord = getenv("T2D_ROW_ORDER");
+    const bool lex = ord && std::string(ord) == "lex";
     std::vector<std::pair<uint64_t, size_t>> order;
-    for (size_t b = 0; b < nblocks; ++b)
-        if (occ[b]) {
-            size_t bx = b % nb[0], by = (b / nb[0]) % nb[1], bz = b / ((size_t)nb[0] * nb[1]);
-            order.emplace_back(spread(bx) | (spread(by) << 1) | (spread(bz) << 2), b);
-        }
-    std::sort(order.begin(), order.end());
-    std::vector<uint4> blocks(nblocks, make_uint4(0, 0, 0, 0));
-    long long base = 0;
-    for (auto& o : order) {
-        unsigned long long w = occ[o.second];
-        blocks[o.second] = make_uint4((unsigned)w, (unsigned)(w >> 32), (unsigned)base, 0);
-        base += __builtin_popcountll(w);
+    for (size_t r = 0; r < nrows; ++r) {
+        bool any = false;
+        for (int w = 0; w < nwx && !any; ++w) any = occ[r * nwx + w] != 0;
+        if (!any) continue;
+        const uint64_t y = r % nc[1], z = r / nc[1];
+        order.emplace_back(lex ? (uint64_t)r : (spread(y) | (spread(z) << 1)), r);
     }
+    std::sort(order.begin(), order.end());
+    std::vector<uint2> words(nwords, make_uint2(0, 0));
+    long long base = 0;
+    for (auto& o : order)
+        for (int w = 0; w < nwx; ++w) {
+            const unsigned bits = occ[o.second * nwx + w];
+            words[o.second * nwx + w] = make_uint2(bits, (unsigned)base);
+            base += __builtin_popcount(bits);
+        }
     if (base > 2000000000LL) throw CudaError{"cell list too large"};
-    d_vox_blocks_.upload(blocks, stream_);
+    d_vox_words_.upload(words, stream_);
     CK(cudaStreamSynchronize(stream_));
     A_.vox.ncx = nc[0];
     A_.vox.ncy = nc[1];
     A_.vox.ncz = nc[2];
-    A_.vox.nbx = nb[0];
-    A_.vox.nby = nb[1];
-    A_.vox.nbz = nb[2];
+    A_.vox.nwx = nwx;
     A_.vox.M = (int)base;
-    A_.vox.blocks = d_vox_blocks_.p;
+    A_.vox.words = d_vox_words_.p;
     for (int k = 0; k < 3; ++k) A_.vox.origin[k] = (R)org[k];
     A_.vox.inv_cell = (R)(1.0 / cs);
     alloc_buckets((int)base + 1);   // + the overflow bucket
@@ -629,7 +636,7 @@ void Engine<R>::ingest(int N, const double* uv, const int* heading, const int* v
     in.vid = vid ? (const int*)put(vid, sizeof(int) * (size_t)N) : nullptr;
     in.r3d = r3d ? (const double*)put(r3d, sizeof(double) * 3 * (size_t)N) : nullptr;
     in.ids = ids ? (const uint32_t*)put(ids, sizeof(uint32_t) * (size_t)N) : nullptr;
-    IoLaunch<R>::ingest(N, in, dst, stream_);
+    IoLaunch<R>::ingest(N, in, dst, d_trig_d_.p, stream_);
     launches_++;
 }
 

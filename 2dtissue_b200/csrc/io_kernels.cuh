@@ -26,7 +26,8 @@ struct HostViewOut {
     uint32_t* ids;
 };
 
-template <typename R> __global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleArrays<R> p)
+template <typename R>
+__global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleArrays<R> p, const double2* __restrict__ trig)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -43,6 +44,17 @@ template <typename R> __global__ void __launch_bounds__(256) k_ingest(int N, Hos
     Real2<R> z = {R(0), R(0)};
     p.rdot[i] = z;
     p.color[i] = 0;
+    if (p.cs) {   // (cos, sin) of the heading as the reference's libm gives them (host-built table), CUDA libm outside it
+        const int n = in.heading ? in.heading[i] : 0;
+        double2 t;
+        if (n >= TRIG_MIN && n <= TRIG_MAX) {
+            t = trig[n - TRIG_MIN];
+        } else {
+            const double r = (double)n * DEG_TO_RAD_D;
+            t = make_double2(cos(r), sin(r));
+        }
+        p.cs[i] = t;
+    }
 }
 
 // slot s holds the particle that sits at index aux[s].w of the caller's arrays.  Slab mode (offsets != null): halo
@@ -119,7 +131,7 @@ template <typename R> __global__ void __launch_bounds__(256) k_outN(int N, int c
 }
 
 template <typename R> struct IoLaunch {
-    static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s);
+    static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, const double2* trig, cudaStream_t s);
     static void egest(int resident, int N, const int* offsets, const ParticleArrays<R>& p, const Real2<R>* F,
                       const int* new_heading, const HostViewOut& out, cudaStream_t s);
     static void owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s);
@@ -129,9 +141,10 @@ template <typename R> struct IoLaunch {
 };
 
 #ifdef T2D_IO_IMPL
-template <typename R> void IoLaunch<R>::ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s)
+template <typename R>
+void IoLaunch<R>::ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, const double2* trig, cudaStream_t s)
 {
-    if (N > 0) k_ingest<R><<<(N + 255) / 256, 256, 0, s>>>(N, in, p);
+    if (N > 0) k_ingest<R><<<(N + 255) / 256, 256, 0, s>>>(N, in, p, trig);
 }
 template <typename R>
 void IoLaunch<R>::egest(int resident, int N, const int* offsets, const ParticleArrays<R>& p, const Real2<R>* F,

@@ -82,8 +82,9 @@ __device__ __forceinline__ void flush_counters(const BlockCounters& c, DevCounte
 }
 
 // ---------------------------------------------------------------------------------------------------
-// sparse voxel index: 3-D cell -> compact bucket id
+// sparse row index: 3-D cell -> compact bucket id, x-run of cells -> one contiguous slot range
 // ---------------------------------------------------------------------------------------------------
+// cell of a point and, per axis, the side of the cell the point lies on (-1: lower half, +1: upper half)
 template <typename R> __device__ __forceinline__ void cell_coords(const DevVox<R>& vx, const Pos3<R>& X, int c[3], int side[3])
 {
     R q[3] = {(X.x - vx.origin[0]) * vx.inv_cell, (X.y - vx.origin[1]) * vx.inv_cell, (X.z - vx.origin[2]) * vx.inv_cell};
@@ -95,55 +96,40 @@ template <typename R> __device__ __forceinline__ void cell_coords(const DevVox<R
     }
 }
 
+// compact index of cell (cx, cy, cz), or -1 if the cell is not in the index
 template <typename R> __device__ __forceinline__ int vox_index(const DevVox<R>& vx, int cx, int cy, int cz)
 {
     if ((unsigned)cx >= (unsigned)vx.ncx || (unsigned)cy >= (unsigned)vx.ncy || (unsigned)cz >= (unsigned)vx.ncz) return -1;
-    const int b = ((cz >> 2) * vx.nby + (cy >> 2)) * vx.nbx + (cx >> 2);
-    const uint4 e = __ldg(&vx.blocks[b]);
-    const unsigned bit = ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3);
-    const unsigned long long bm = ((unsigned long long)e.y << 32) | e.x;
-    if (!((bm >> bit) & 1ull)) return -1;
-    return (int)e.z + __popcll(bm & ((1ull << bit) - 1ull));
+    const uint2 e = __ldg(&vx.words[((size_t)cz * vx.ncy + cy) * vx.nwx + (cx >> 5)]);
+    const unsigned bit = cx & 31;
+    if (!((e.x >> bit) & 1u)) return -1;
+    return (int)e.y + __popc(e.x & ((1u << bit) - 1u));
 }
 
-// x-run lookup for the stencil: cells (x0, y, z) and (x0 + 1, y, z).  Compact indices are x-fastest inside a 4x4x4
-// block, so when both cells sit in one block their particles form ONE contiguous range
-// [start[i0], start[i0 + o0 + o1]); otherwise the two cells are looked up separately.  Appends the non-empty
-// ranges to this thread's column of the shared range table.
-template <typename R, int NT>
-__device__ __forceinline__ void vox_row_ranges(const StepArgs<R>& a, int x0, int y, int z, int (*s_beg)[NT], int (*s_end)[NT],
-                                               int tid, int& nr)
+// slot range [b, e) of the particles in cells (x0, y, z) and (x0 + 1, y, z).  Compact indices ascend along x
+// inside a row (also across its words), so the two cells' particles are contiguous in the sorted state whether or
+// not both are occupied.  Empty (b == e) outside the grid.
+template <typename R> __device__ __forceinline__ void row_range(const StepArgs<R>& a, int x0, int y, int z, int& b, int& e)
 {
     const DevVox<R>& vx = a.vox;
-    if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz) return;
-    if ((x0 & 3) != 3 && (unsigned)x0 < (unsigned)(vx.ncx - 1)) {
-        const int b = ((z >> 2) * vx.nby + (y >> 2)) * vx.nbx + (x0 >> 2);
-        const uint4 e = __ldg(&vx.blocks[b]);
-        const unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x0 & 3);
-        const unsigned long long bm = ((unsigned long long)e.y << 32) | e.x;
-        const int occ = (int)((bm >> bit) & 3ull);   // bit 0: cell x0, bit 1: cell x0 + 1
-        if (occ) {
-            const int i0 = (int)e.z + __popcll(bm & ((1ull << bit) - 1ull));
-            const int sb = a.start[i0], se = a.start[i0 + (occ & 1) + (occ >> 1)];
-            if (se > sb) {
-                s_beg[nr][tid] = sb;
-                s_end[nr][tid] = se;
-                nr++;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int idx = vox_index<R>(vx, x0 + q, y, z);
-            if (idx >= 0) {
-                const int sb = a.start[idx], se = a.start[idx + 1];
-                if (se > sb) {
-                    s_beg[nr][tid] = sb;
-                    s_end[nr][tid] = se;
-                    nr++;
-                }
-            }
-        }
+    b = e = 0;
+    if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz || (unsigned)x0 >= (unsigned)(vx.ncx - 1)) return;
+    const uint2* w = vx.words + ((size_t)z * vx.ncy + y) * vx.nwx + (x0 >> 5);
+    const uint2 e0 = __ldg(w);
+    const unsigned bit = x0 & 31;
+    int lo, hi;
+    if (bit != 31) {
+        const unsigned m2 = 0xffffffffu >> (30 - bit);   // bits 0 .. bit + 1
+        lo = (int)e0.y + __popc(e0.x & (m2 >> 2));
+        hi = (int)e0.y + __popc(e0.x & m2);
+    } else {   // the run straddles two words of the row
+        const uint2 e1 = __ldg(w + 1);
+        lo = (int)e0.y + __popc(e0.x & 0x7fffffffu);
+        hi = (int)e1.y + (int)(e1.x & 1u);
+    }
+    if (hi > lo) {
+        b = a.start[lo];
+        e = a.start[hi];
     }
 }
 
@@ -171,7 +157,7 @@ template <typename R> __device__ __forceinline__ uint32_t bucket_key(const StepA
 // setup: voxelise the mesh surface into the sparse cell index.  One warp per face; lanes stride over the
 // cells of the face's (grown) bounding box and mark those whose centre is within `reach` of the triangle
 // (reach = half a cell diagonal + tolerance, so every cell the triangle touches is marked).
-// occ: one 64-bit occupancy word per 4x4x4 block.
+// occ: one 32-bit occupancy word per 32 cells of a row.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double point_triangle_dist2_3d(const double p[3], const double a[3], const double b[3], const double c[3])
 {
@@ -206,7 +192,7 @@ __device__ __forceinline__ double point_triangle_dist2_3d(const double p[3], con
 
 template <typename R>
 __global__ void __launch_bounds__(256) k_voxelize(DevMesh<R> m, double ox, double oy, double oz, double cs, double reach,
-                                                  int ncx, int ncy, int ncz, int nbx, int nby, unsigned long long* occ)
+                                                  int ncx, int ncy, int ncz, int nwx, unsigned* occ)
 {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -229,11 +215,8 @@ __global__ void __launch_bounds__(256) k_voxelize(DevMesh<R> m, double ox, doubl
         for (long long q = lane; q < total; q += 32) {
             const int cx = lo[0] + (int)(q % ex), cy = lo[1] + (int)((q / ex) % ey), cz = lo[2] + (int)(q / ((long long)ex * ey));
             const double p[3] = {ox + (cx + 0.5) * cs, oy + (cy + 0.5) * cs, oz + (cz + 0.5) * cs};
-            if (point_triangle_dist2_3d(p, a, b, c) <= reach * reach) {
-                const size_t blk = ((size_t)(cz >> 2) * nby + (cy >> 2)) * nbx + (cx >> 2);
-                const unsigned bit = ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3);
-                atomicOr(&occ[blk], 1ull << bit);
-            }
+            if (point_triangle_dist2_3d(p, a, b, c) <= reach * reach)
+                atomicOr(&occ[((size_t)cz * ncy + cy) * nwx + (cx >> 5)], 1u << (cx & 31));
         }
     }
 }
@@ -270,6 +253,7 @@ template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<
     a.alt.aux[s] = a.cur.aux[i];
     a.alt.rdot[s] = a.cur.rdot[i];
     a.alt.color[s] = a.cur.color[i];
+    if (a.cur.cs) a.alt.cs[s] = a.cur.cs[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -418,19 +402,24 @@ __device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> 
 // ---------------------------------------------------------------------------------------------------
 // K3-K5 fused (Euclidean criterion).  d_ij = ||X_i - X_j|| on the 3-D positions of the previous projection.
 // Cell edge = 2*rmax: a neighbour within rmax lies in the particle's own cell or the adjacent one on the
-// nearer side per axis -> 8 cells, whose particle ranges are contiguous in the sorted state; the 8 ranges
-// (+ the overflow bucket) are walked as ONE flat candidate loop so that lanes do not idle on short cells.
-// EXACT (fp64 parity path): the in-range neighbours are gathered, sorted by global id and summed in that
-// order (the reference sums in ascending j), so forces are bit-identical; rows longer than KMAX fall back
-// to unordered sums (counted).  The fast path sums in visiting order.
+// nearer side per axis -> 2x2 rows of 2 x-adjacent cells; a row's 2 cells are ONE contiguous slot range of the
+// sorted state (row_range), so a particle walks 4 ranges (+ the overflow bucket, normally empty).
 // One thread per particle; the new state goes to `alt` (other particles still read `cur`), together with
 // the particle's next bucket key, arrival rank and the histogram for the counting sort that follows.
+//
+//   k_step_euclid_exact  fp64 parity path: the in-range neighbours are gathered, sorted by global id and summed in
+//                        that order (the reference sums in ascending j), so forces are bit-identical; rows longer
+//                        than KMAX are ordered by repeated selection (still exact, counted).
+//   k_step_euclid_fast   fp32 fast path: predicates on squared distances, one rsqrt per in-range pair, sums in
+//                        visiting order, (cos, sin) of the neighbours' headings from the per-particle `cs` array,
+//                        UV point location deferred to a CTA-wide compacted pass for the particles that left
+//                        their previous face.
 // ---------------------------------------------------------------------------------------------------
 constexpr int EUCLID_KMAX = 48;
 constexpr int STEP_THREADS = 128;
-constexpr int NRANGE = 9;
+constexpr int NRANGE = 5;
 
-template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, EXACT ? 4 : 8) k_step_euclid(StepArgs<R> a)
+template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 4) k_step_euclid_exact(StepArgs<R> a)
 {
     __shared__ int s_beg[NRANGE][STEP_THREADS];
     __shared__ int s_end[NRANGE][STEP_THREADS];
@@ -451,9 +440,15 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
             cell_coords<R>(a.vox, Pi, c, side);
             const int x0 = side[0] < 0 ? c[0] - 1 : c[0];
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
-                vox_row_ranges<R, STEP_THREADS>(a, x0, c[1] + ((m & 1) ? side[1] : 0), c[2] + ((m & 2) ? side[2] : 0), s_beg, s_end,
-                                                tid, nr);
+            for (int m = 0; m < 4; ++m) {
+                int rb, re;
+                row_range<R>(a, x0, c[1] + ((m & 1) ? side[1] : 0), c[2] + ((m & 2) ? side[2] : 0), rb, re);
+                if (re > rb) {
+                    s_beg[nr][tid] = rb;
+                    s_end[nr][tid] = re;
+                    nr++;
+                }
+            }
             const int ob = a.start[a.vox.M], oe = a.start[a.vox.M + 1];   // overflow bucket: normally empty
             if (oe > ob) {
                 s_beg[nr][tid] = ob;
@@ -468,65 +463,58 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
         int color = 0;
         int npairs = 0;
 
-        if constexpr (!EXACT) {
-            // fast path: predicates on squared distances, one rsqrt per in-range pair, sums in visiting order; the
-            // candidate ranges are walked as one flat loop with the next candidate's load issued one iteration ahead
-            // (measured: a two-phase variant with a per-thread hit list in shared memory was 12 % slower)
-            const float r2s = a.two_sigma * a.two_sigma, r2c = a.color_r * a.color_r;
-            const float inv2s = 1.0f / a.two_sigma;
-            auto pair_body = [&](int j, const Pos3<R>& Pj, float d2) {
-                const double2 t = trig_lookup(a.trig_d, (int)Pj.w, bc.trig_fb);
-                mx += t.x;
-                my += t.y;
-                if (j != i) {
-                    npairs++;
-                    float rinv = rsqrtf(d2), d = d2 * rinv;
-                    if (d2 == 0.0f) {   // coincident particles: d := 0.001 (ForceHelper.cpp:59-62)
-                        d = 0.001f;
-                        rinv = 1000.0f;
-                    }
-                    const float g = -a.k * (a.two_sigma - d) * inv2s * rinv;   // F_ij / d
-                    const Real2<R> uj = a.cur.uv[j];
-                    fx += g * (ui.x - uj.x);
-                    fy += g * (ui.y - uj.y);
+        unsigned long long list[EUCLID_KMAX];
+        int cnt = 0;
+        bool overflow = false;
+        // pass 1: every candidate once: colour, cutoff ties, list of in-range neighbours
+        {
+            int m = 0, j = nr > 0 ? s_beg[0][tid] : 0, e = nr > 0 ? s_end[0][tid] : 0;
+            for (;;) {
+                while (j >= e && m < nr - 1) {
+                    ++m;
+                    j = s_beg[m][tid];
+                    e = s_end[m][tid];
                 }
-            };
-            int m = 0, jn = 0, e = 0;
-            bool have = nr > 0;
-            Pos3<R> Pn = Pi;
-            if (have) {
-                jn = s_beg[0][tid];
-                e = s_end[0][tid];
-                Pn = a.cur.pos[jn];
-            }
-            while (have) {
-                const int j = jn;
-                const Pos3<R> Pj = Pn;
-                // advance and issue the next candidate's load before working on this one
-                if (++jn >= e) {
-                    if (++m < nr) {
-                        jn = s_beg[m][tid];
-                        e = s_end[m][tid];
-                    } else {
-                        have = false;
-                    }
-                }
-                if (have) Pn = a.cur.pos[jn];
-                const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
-                const float d2 = dx * dx + dy * dy + dz * dz;
+                if (j >= e) break;
+                const Pos3<R> Pj = a.cur.pos[j];
+                const R dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                const R d2 = dx * dx + dy * dy + dz * dz;
                 if (d2 <= rmax2) {
-                    color += (j != i && d2 > 0.0f && d2 <= r2c) ? 1 : 0;   // _2DTissue::count_particle_neighbors
-                    if (d2 < r2s) pair_body(j, Pj, d2);
+                    const R d = (j == i) ? R(0) : rsqrt_exact<R>(d2);
+                    if (d != R(0) && d <= a.color_r) color++;   // _2DTissue::count_particle_neighbors
+                    if (d == a.two_sigma) bc.ties_cut++;
+                    if (d < a.two_sigma) {
+                        if (cnt < EUCLID_KMAX) list[cnt] = ((unsigned long long)(uint32_t)a.cur.aux[j].z << 32) | (unsigned)j;
+                        cnt++;
+                    }
                 }
+                ++j;
             }
         }
-
-        if constexpr (EXACT) {
-            unsigned long long list[EUCLID_KMAX];
-            int cnt = 0;
-            bool overflow = false;
-            // pass 1: every candidate once: colour, cutoff ties, list of in-range neighbours
-            {
+        overflow = cnt > EUCLID_KMAX;
+        if ((unsigned long long)cnt > bc.max_row) bc.max_row = cnt;
+        if (!overflow) {
+            for (int p = 1; p < cnt; ++p) {   // insertion sort by (id, slot)
+                unsigned long long kx = list[p];
+                int q = p - 1;
+                while (q >= 0 && list[q] > kx) {
+                    list[q + 1] = list[q];
+                    --q;
+                }
+                list[q + 1] = kx;
+            }
+        } else {
+            bc.order_fb++;   // long row: ordered by repeated selection instead of the register list (still exact)
+        }
+        // pass 2: accumulate in ascending global id, the reference's summation order
+        unsigned long long last = 0;
+        bool first = true;
+        for (int p = 0; p < cnt; ++p) {
+            int jj;
+            if (!overflow) {
+                jj = (int)(unsigned)list[p];
+            } else {   // smallest (id, slot) key above `last` among the in-range candidates
+                unsigned long long best = ~0ull;
                 int m = 0, j = nr > 0 ? s_beg[0][tid] : 0, e = nr > 0 ? s_end[0][tid] : 0;
                 for (;;) {
                     while (j >= e && m < nr - 1) {
@@ -540,79 +528,31 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
                     const R d2 = dx * dx + dy * dy + dz * dz;
                     if (d2 <= rmax2) {
                         const R d = (j == i) ? R(0) : rsqrt_exact<R>(d2);
-                        if (d != R(0) && d <= a.color_r) color++;   // _2DTissue::count_particle_neighbors
-                        if (d == a.two_sigma) bc.ties_cut++;
                         if (d < a.two_sigma) {
-                            if (cnt < EUCLID_KMAX) list[cnt] = ((unsigned long long)(uint32_t)a.cur.aux[j].z << 32) | (unsigned)j;
-                            cnt++;
+                            unsigned long long key = ((unsigned long long)(uint32_t)a.cur.aux[j].z << 32) | (unsigned)j;
+                            if ((first || key > last) && key < best) best = key;
                         }
                     }
                     ++j;
                 }
+                last = best;
+                first = false;
+                jj = (int)(unsigned)best;
             }
-            overflow = cnt > EUCLID_KMAX;
-            if ((unsigned long long)cnt > bc.max_row) bc.max_row = cnt;
-            if (!overflow) {
-                for (int p = 1; p < cnt; ++p) {   // insertion sort by (id, slot)
-                    unsigned long long kx = list[p];
-                    int q = p - 1;
-                    while (q >= 0 && list[q] > kx) {
-                        list[q + 1] = list[q];
-                        --q;
-                    }
-                    list[q + 1] = kx;
-                }
-            } else {
-                bc.order_fb++;   // long row: ordered by repeated selection instead of the register list (still exact)
-            }
-            // pass 2: accumulate in ascending global id, the reference's summation order
-            unsigned long long last = 0;
-            bool first = true;
-            for (int p = 0; p < cnt; ++p) {
-                int jj;
-                if (!overflow) {
-                    jj = (int)(unsigned)list[p];
-                } else {   // smallest (id, slot) key above `last` among the in-range candidates
-                    unsigned long long best = ~0ull;
-                    int m = 0, j = nr > 0 ? s_beg[0][tid] : 0, e = nr > 0 ? s_end[0][tid] : 0;
-                    for (;;) {
-                        while (j >= e && m < nr - 1) {
-                            ++m;
-                            j = s_beg[m][tid];
-                            e = s_end[m][tid];
-                        }
-                        if (j >= e) break;
-                        const Pos3<R> Pj = a.cur.pos[j];
-                        const R dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
-                        const R d2 = dx * dx + dy * dy + dz * dz;
-                        if (d2 <= rmax2) {
-                            const R d = (j == i) ? R(0) : rsqrt_exact<R>(d2);
-                            if (d < a.two_sigma) {
-                                unsigned long long key = ((unsigned long long)(uint32_t)a.cur.aux[j].z << 32) | (unsigned)j;
-                                if ((first || key > last) && key < best) best = key;
-                            }
-                        }
-                        ++j;
-                    }
-                    last = best;
-                    first = false;
-                    jj = (int)(unsigned)best;
-                }
-                const Pos3<R> Pj = a.cur.pos[jj];
-                const R dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
-                const R d = (jj == i) ? R(0) : rsqrt_exact<R>(dx * dx + dy * dy + dz * dz);
-                const double2 t = trig_lookup(a.trig_d, (int)Pj.w, bc.trig_fb);
-                mx += t.x;
-                my += t.y;
-                if (jj != i) {
-                    npairs++;
-                    R dd = d;
-                    if (dd == R(0)) dd += R(0.001);   // ForceHelper.cpp:59-62
-                    const R Fij = pair_fij<R>(a.k, a.two_sigma, dd);
-                    const Real2<R> uj = a.cur.uv[jj];
-                    fx += Fij * ((ui.x - uj.x) / dd);
-                    fy += Fij * ((ui.y - uj.y) / dd);
-                }
+            const Pos3<R> Pj = a.cur.pos[jj];
+            const R dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+            const R d = (jj == i) ? R(0) : rsqrt_exact<R>(dx * dx + dy * dy + dz * dz);
+            const double2 t = trig_lookup(a.trig_d, (int)Pj.w, bc.trig_fb);
+            mx += t.x;
+            my += t.y;
+            if (jj != i) {
+                npairs++;
+                R dd = d;
+                if (dd == R(0)) dd += R(0.001);   // ForceHelper.cpp:59-62
+                const R Fij = pair_fij<R>(a.k, a.two_sigma, dd);
+                const Real2<R> uj = a.cur.uv[jj];
+                fx += Fij * ((ui.x - uj.x) / dd);
+                fy += Fij * ((ui.y - uj.y) / dd);
             }
         }
         bc.pairs += (unsigned long long)npairs;
@@ -629,6 +569,7 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
             a.alt.aux[i] = make_int4(vid, face, ai.z, ai.w);
             a.alt.rdot[i] = rd;
             a.alt.color[i] = color;
+            if (a.alt.cs) a.alt.cs[i] = trig_lookup(a.trig_d, n_new, bc.trig_fb);
             if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
                 const uint32_t key = bucket_key<R>(a, X, vid, bc);
                 a.key[i] = key;
@@ -642,6 +583,213 @@ template <typename R, bool EXACT, bool MOVING> __global__ void __launch_bounds__
         }
     }
     flush_counters(bc, a.counters);
+}
+
+// ---- fp32 fast path -----------------------------------------------------------------------------------
+// first face of the point's grid cell (ascending id) that contains it: the reference's arg-min of (distance, face id)
+// for every point that is not within rounding of an edge; -1 if none does (the caller then takes the arg-min itself)
+__device__ __forceinline__ int locate_face_contains(const DevMesh<float>& m, float px, float py)
+{
+    const int G = m.G;
+    int gi = (int)floorf(px * (float)G), gj = (int)floorf(py * (float)G);
+    gi = gi < 0 ? 0 : (gi > G - 1 ? G - 1 : gi);
+    gj = gj < 0 ? 0 : (gj > G - 1 ? G - 1 : gj);
+    const int cell = gj * G + gi;
+    const int qs = __ldg(&m.gstart[cell]), qe = __ldg(&m.gstart[cell + 1]);
+    for (int q = qs; q < qe; ++q) {
+        const int f = __ldg(&m.gfaces[q]);
+        const TriUV<float> t = m.tri[f];
+        const float ex = t.ax - px, ey = t.ay - py, fx = t.bx - px, fy = t.by - py, gx = t.cx - px, gy = t.cy - py;
+        const float wa = fx * gy - fy * gx, wb = gx * ey - gy * ex, wc = ex * fy - ey * fx;   // 2 * signed sub-areas
+        if ((wa >= 0.0f && wb >= 0.0f && wc >= 0.0f) || (wa <= 0.0f && wb <= 0.0f && wc <= 0.0f)) return f;
+    }
+    return -1;
+}
+
+struct FastSmem {
+    float px[STEP_THREADS], py[STEP_THREADS];
+    int face[STEP_THREADS];
+    int queue[STEP_THREADS];
+    int nq;
+};
+
+template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step_euclid_fast(StepArgs<float> a)
+{
+    typedef float R;
+    __shared__ FastSmem sm;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * STEP_THREADS + tid;
+    if (MOVING && tid == 0) sm.nq = 0;
+    const bool resident = i < resident_count<R>(a);
+    const int4 ai = resident ? a.cur.aux[i] : make_int4(0, 0, 0, ORIGIN_DEAD);
+    const bool live = resident && ai.w >= 0;   // slab mode: halo copies are read by others, never advanced
+    if (MOVING && resident && !live) a.alt.aux[i] = make_int4(0, -1, ai.z, ORIGIN_DEAD);
+
+    unsigned npairs = 0, nties = 0;
+    Real2<R> ui = {0.0f, 0.0f}, rd = {0.0f, 0.0f}, p = {0.0f, 0.0f};
+    int n_new = 0, color = 0, hint = -1;
+    bool need_locate = false;
+    float fx = 0.0f, fy = 0.0f;
+
+    if (live) {
+        const Pos3<R> Pi = a.cur.pos[i];
+        const double2 own = a.cur.cs[i];
+        ui = a.cur.uv[i];
+        int rb[4], re[4];
+        {
+            int c[3], side[3];
+            cell_coords<R>(a.vox, Pi, c, side);
+            const int x0 = side[0] < 0 ? c[0] - 1 : c[0];
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                row_range<R>(a, x0, c[1] + ((m & 1) ? side[1] : 0), c[2] + ((m & 2) ? side[2] : 0), rb[m], re[m]);
+        }
+        const int ob = a.start[a.vox.M], oe = a.start[a.vox.M + 1];   // overflow bucket: normally empty
+        const float r2s = a.two_sigma * a.two_sigma, r2c = a.color_r * a.color_r;
+        const float gk = -a.k / a.two_sigma;
+        double mx = 0.0, my = 0.0;
+        int nzero = 0;   // candidates at distance 0 (the particle itself and coincident ones): never coloured
+        const Pos3<R>* __restrict__ pos = a.cur.pos;
+        const double2* __restrict__ cs = a.cur.cs;
+        const Real2<R>* __restrict__ uv = a.cur.uv;
+        auto scan = [&](int jb, int je) {
+            for (int j = jb; j < je; ++j) {
+                const Pos3<R> Pj = pos[j];
+                const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                color += (d2 <= r2c) ? 1 : 0;   // _2DTissue::count_particle_neighbors (distance-0 candidates removed below)
+                if (d2 < r2s) {
+                    const double2 t = cs[j];
+                    const Real2<R> uj = uv[j];
+                    mx += t.x;
+                    my += t.y;
+                    npairs++;
+                    float rinv = rsqrtf(d2), d = d2 * rinv;
+                    if (d2 == 0.0f) {   // itself (force term vanishes: ui - uj = 0) or a coincident particle: d := 0.001 (ForceHelper.cpp:59-62)
+                        d = 0.001f;
+                        rinv = 1000.0f;
+                        nzero++;
+                    }
+                    const float g = gk * (a.two_sigma - d) * rinv;   // F_ij / d
+                    fx += g * (ui.x - uj.x);
+                    fy += g * (ui.y - uj.y);
+                }
+            }
+        };
+#pragma unroll
+        for (int m = 0; m < 4; ++m) scan(rb[m], re[m]);
+        if (oe > ob) scan(ob, oe);
+        if (r2s > 0.0f) {
+            color -= nzero;
+            npairs -= 1;   // itself
+        } else {
+            color -= 1;
+        }
+
+        // speed and velocity (Locomotion.cpp:71-81): own heading's unit vector from the cs array
+        const float absF = sqrtf(fx * fx + fy * fy) + a.v0;
+        rd.x = (float)own.x * absF;
+        rd.y = (float)own.y * absF;
+        // heading after alignment (+ noise); the sums are doubles on this path too (see heading_from_sum)
+        {
+            BlockCounters hc;
+            n_new = heading_from_sum<R>(a, mx, my, (uint32_t)ai.z, hc);
+            nties = (unsigned)hc.ties_trunc;
+        }
+        if (MOVING) {
+            p.x = ui.x + rd.x * a.step_size;   // Locomotion.cpp:84
+            p.y = ui.y + rd.y * a.step_size;
+            Real2<R> old = ui;
+            int wraps = 0;
+            const bool cap = seam_reentry<R>(old.x, old.y, p.x, p.y, n_new, wraps);
+            unsigned fault = 0;
+            if (wraps) atomicAdd(&a.counters->wraps, (unsigned long long)wraps);
+            if (cap) {
+                atomicAdd(&a.counters->wrap_cap_hits, 1ull);
+                fault |= T2D_FAULT_WRAP_CAP;
+            }
+            if (!inside_square<R>(p.x, p.y)) {   // Validation::error_lost_particles
+                atomicAdd(&a.counters->lost, 1ull);
+                fault |= T2D_FAULT_LOST;
+            }
+            if (!isfinite(p.x) || !isfinite(p.y)) {   // Validation::error_invalid_values
+                atomicAdd(&a.counters->nonfinite, 1ull);
+                fault |= T2D_FAULT_NONFINITE;
+            }
+            if (fault) atomicOr(&a.counters->fault, fault);
+            hint = wraps == 0 ? ai.y : -1;
+            need_locate = true;
+            if (hint >= 0) need_locate = !hint_contains(a.mesh.tri[hint], p.x, p.y);
+        }
+    }
+
+    if (MOVING) {
+        // the particles that left their previous face are located by the first threads of the CTA, densely packed
+        __syncthreads();   // sm.nq = 0 visible
+        if (need_locate) {
+            const int q = atomicAdd(&sm.nq, 1);
+            sm.queue[q] = tid;
+            sm.px[tid] = p.x;
+            sm.py[tid] = p.y;
+        }
+        __syncthreads();
+        if (tid < sm.nq) {
+            const int o = sm.queue[tid];
+            sm.face[o] = locate_face_contains(a.mesh, sm.px[o], sm.py[o]);
+        }
+        __syncthreads();
+        if (live) {
+            int f = hint;
+            if (need_locate) {
+                f = sm.face[tid];
+                if (f < 0) {   // within rounding of an edge (or outside every listed face): the reference's arg-min over distances
+                    BlockCounters lc;
+                    f = locate_face<R>(a.mesh, p.x, p.y, lc);
+                    if (lc.loc_fb) atomicAdd(&a.counters->locate_fallbacks, lc.loc_fb);
+                }
+            }
+            const TriUV<R> t = a.mesh.tri[f];
+            const int4 tv = a.mesh.tri_vid[f];
+            const Pos3<R> A = a.mesh.x3d[tv.x], B = a.mesh.x3d[tv.y], C = a.mesh.x3d[tv.z];
+            const R Av[3] = {A.x, A.y, A.z}, Bv[3] = {B.x, B.y, B.z}, Cv[3] = {C.x, C.y, C.z};
+            R Xv[3];
+            const int which = lift_to_3d<R>(p.x, p.y, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv);
+            const int vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
+            const Pos3<R> X = {Xv[0], Xv[1], Xv[2], (R)n_new};
+            unsigned long long tfb = 0;
+            const double2 ncs = trig_lookup(a.trig_d, n_new, tfb);
+            if (tfb) atomicAdd(&a.counters->trig_fallbacks, tfb);
+            a.alt.pos[i] = X;
+            a.alt.uv[i] = p;
+            a.alt.aux[i] = make_int4(vid, f, ai.z, ai.w);
+            a.alt.rdot[i] = rd;
+            a.alt.color[i] = color;
+            a.alt.cs[i] = ncs;
+            if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
+                int c[3], side[3];
+                cell_coords<R>(a.vox, X, c, side);
+                int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
+                if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket
+                    atomicAdd(&a.counters->cell_fallbacks, 1ull);
+                    idx = a.vox.M;
+                }
+                a.key[i] = (uint32_t)idx;
+                a.rank[i] = (uint32_t)atomicAdd(&a.count[idx], 1);
+            }
+        }
+    } else if (live) {   // t2d_forces: report without moving
+        Real2<R> Fv = {fx, fy};
+        a.F[i] = Fv;
+        a.new_heading[i] = n_new;
+        a.cur.color[i] = color;
+    }
+    // diagnostic counters: one atomic per warp
+    npairs = __reduce_add_sync(0xffffffffu, npairs);
+    nties = __reduce_add_sync(0xffffffffu, nties);
+    if ((tid & 31) == 0) {
+        if (npairs) atomicAdd(&a.counters->pairs_in_range, (unsigned long long)npairs);
+        if (nties) atomicAdd(&a.counters->ties_trunc, (unsigned long long)nties);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -997,6 +1145,7 @@ template <typename R> __global__ void __launch_bounds__(256) k_comm_unpack(StepA
             a.cur.aux[slot] = make_int4(0, -1, g.id, ORIGIN_GHOST);
             a.cur.color[slot] = 0;
         }
+        if (a.cur.cs) a.cur.cs[slot] = trig_lookup(a.trig_d, (int)P.w, bc.trig_fb);
         const uint32_t key = bucket_key<R>(a, P, vid, bc);
         a.key[slot] = key;
         a.rank[slot] = (uint32_t)atomicAdd(&a.count[key], 1);
@@ -1091,12 +1240,12 @@ template <typename R> __global__ void __launch_bounds__(256) k_unit_vectors(Step
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 template <typename R>
-void Launch<R>::voxelize(const DevMesh<R>& m, const double org[3], double cs, double reach, const int nc[3], int nbx, int nby,
-                         unsigned long long* occ, cudaStream_t s)
+void Launch<R>::voxelize(const DevMesh<R>& m, const double org[3], double cs, double reach, const int nc[3], int nwx,
+                         unsigned* occ, cudaStream_t s)
 {
     int grid = div_up(m.F * 32, 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    k_voxelize<R><<<grid, 256, 0, s>>>(m, org[0], org[1], org[2], cs, reach, nc[0], nc[1], nc[2], nbx, nby, occ);
+    k_voxelize<R><<<grid, 256, 0, s>>>(m, org[0], org[1], org[2], cs, reach, nc[0], nc[1], nc[2], nwx, occ);
 }
 // slab mode: the resident count lives on the device and changes every step; grids cover the context's capacity
 template <typename R> static int launch_extent(const StepArgs<R>& a) { return a.comm.on ? a.comm.capacity : a.N; }
@@ -1115,11 +1264,18 @@ template <typename R> void Launch<R>::step_euclid(const StepArgs<R>& a, bool mov
 {
     const int n = launch_extent<R>(a);
     if (n <= 0) return;
-    constexpr bool EXACT = sizeof(R) == 8;
-    if (moving)
-        k_step_euclid<R, EXACT, true><<<div_up(n, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
-    else
-        k_step_euclid<R, EXACT, false><<<div_up(n, STEP_THREADS), STEP_THREADS, 0, s>>>(a);
+    const int grid = div_up(n, STEP_THREADS);
+    if constexpr (sizeof(R) == 4) {
+        if (moving)
+            k_step_euclid_fast<true><<<grid, STEP_THREADS, 0, s>>>(a);
+        else
+            k_step_euclid_fast<false><<<grid, STEP_THREADS, 0, s>>>(a);
+    } else {
+        if (moving)
+            k_step_euclid_exact<R, true><<<grid, STEP_THREADS, 0, s>>>(a);
+        else
+            k_step_euclid_exact<R, false><<<grid, STEP_THREADS, 0, s>>>(a);
+    }
 }
 template <typename R> void Launch<R>::comm_pack(const StepArgs<R>& a, cudaStream_t s)
 {

@@ -37,16 +37,18 @@ struct DevCSR {
     const double* d = nullptr;    // [nnz]
 };
 
-// Sparse voxel index of the 3-D cell list (Euclidean criterion).  Particles live ON the mesh surface, so the
-// set of cells that can ever hold a particle is static: the cells within half a cell diagonal of a mesh
-// triangle.  Cells are grouped in 4x4x4 blocks; a block stores a 64-bit occupancy map and the compact index
-// of its first occupied cell.  Blocks are numbered along a Morton curve, so compact cell indices — the sort
-// key of the counting sort — are spatially coherent and the bucket arrays have M ~ N entries.
+// Sparse row index of the 3-D cell list (Euclidean criterion).  Particles live ON the mesh surface, so the set of
+// cells that can ever hold a particle is static: the cells within half a cell diagonal of a mesh triangle.  The
+// grid is cut into rows along x; a row is a string of 32-cell words {occupancy bits, compact index of the word's
+// first occupied cell}.  Compact indices — the sort key of the counting sort — ascend along x inside a row and
+// rows follow a Morton curve over (y, z): the particles of ANY run of x-adjacent cells are one contiguous slot
+// range [start[rank(x0)], start[rank(x1 + 1)]), found with one 8-byte load and two popcounts, and the bucket
+// arrays have M ~ N entries.
 template <typename R> struct DevVox {
     int ncx = 0, ncy = 0, ncz = 0;     // cells per axis
-    int nbx = 0, nby = 0, nbz = 0;     // blocks per axis
+    int nwx = 0;                       // 32-cell words per row
     int M = 0;                         // compact cells; bucket M is the overflow bucket (cell not in the index)
-    const uint4* blocks = nullptr;     // [nbx*nby*nbz] {occupancy lo, occupancy hi, base, 0}
+    const uint2* words = nullptr;      // [ncz*ncy*nwx] {occupancy, base}
     R origin[3] = {0, 0, 0};
     R inv_cell = 0;
 };
@@ -59,6 +61,7 @@ template <typename R> struct ParticleArrays {
     int4* aux = nullptr;      // x = nearest-vertex id (vertices_3D_active), y = face, z = global id, w = index in the caller's arrays
     Real2<R>* rdot = nullptr; // velocity of the last step (r_dot)
     int* color = nullptr;     // neighbour count of the last step (particles_color)
+    double2* cs = nullptr;    // fp32 Euclid path only: (cos, sin) of the heading as the reference's libm gives them
 };
 
 // ---- multi-GPU slabs: message records and the device-side description of one rank's slab ----
@@ -132,8 +135,8 @@ template <typename R> struct StepArgs {
 
 // kernel launchers implemented once per precision (step_f64.cu with --fmad=false, step_f32.cu with FMA)
 template <typename R> struct Launch {
-    static void voxelize(const DevMesh<R>& m, const double org[3], double cs, double reach, const int nc[3], int nbx, int nby,
-                         unsigned long long* occ, cudaStream_t s);   // setup: surface cells of the sparse voxel index
+    static void voxelize(const DevMesh<R>& m, const double org[3], double cs, double reach, const int nc[3], int nwx,
+                         unsigned* occ, cudaStream_t s);   // setup: surface cells of the sparse row index
     static void bin(const StepArgs<R>& a, cudaStream_t s);                      // key + rank + histogram of `cur`
     static void scatter(const StepArgs<R>& a, cudaStream_t s);                  // cur -> alt in bucket order
     static void step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s); // stages 2-5 fused, cur -> alt (+ next keys)
