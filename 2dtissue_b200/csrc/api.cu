@@ -5,6 +5,7 @@
 // buffered for the counting sort) and the staging areas for the reference-layout host arrays.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -493,7 +494,7 @@ template <typename R> void Engine<R>::alloc_buckets(int nbuckets)
     A_.blocksums = d_blocksums_.p;
 }
 
-// Sparse row index of the 3-D cell list (t2d_internal.h DevVox).  Cell edge = 2*rmax*(1+margin); the cells a
+// Sparse row index of the 3-D cell list (t2d_internal.h DevVox).  Cell edge = rmax*(1+margin); the cells a
 // particle can ever occupy are those the mesh surface touches (positions are convex combinations of a face's
 // corners, CellHelper.cpp:143-146), found by a GPU voxelisation.  Compact indices ascend along x inside a row; the
 // rows follow a Morton curve over (y, z) (T2D_ROW_ORDER=lex: plain (z, y) order, for A/B measurements).
@@ -502,7 +503,7 @@ template <typename R> void Engine<R>::build_vox()
     const double two_sigma = 2 * P_.sigma, color_r = P_.color_factor * P_.sigma;
     const double rmax = std::max(two_sigma, color_r);
     const double margin = sizeof(R) == 8 ? 1e-9 : 1e-3;
-    const double cs = 2.0 * rmax * (1.0 + margin);
+    const double cs = rmax * (1.0 + margin);
     if (!(cs > 0)) throw CudaError{"sigma must be positive"};
     double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
     for (int v = 0; v < chart_.V; ++v)
@@ -520,7 +521,7 @@ template <typename R> void Engine<R>::build_vox()
         nc[k] = (int)n;
         extent = std::max(extent, mx[k] - mn[k]);
     }
-    const int nwx = (nc[0] + 31) / 32;
+    const int nwx = (nc[0] >> 5) + 1;   // + a spare word at the end of every row (row_range reads rank(ncx))
     const size_t nrows = (size_t)nc[1] * nc[2];
     const double nwords_d = (double)nrows * nwx;
     if (nwords_d > 7.5e8) throw CudaError{"sigma is too small for the mesh extent (the row table of the cell list would exceed 6 GB)"};

@@ -84,16 +84,12 @@ __device__ __forceinline__ void flush_counters(const BlockCounters& c, DevCounte
 // ---------------------------------------------------------------------------------------------------
 // sparse row index: 3-D cell -> compact bucket id, x-run of cells -> one contiguous slot range
 // ---------------------------------------------------------------------------------------------------
-// cell of a point and, per axis, the side of the cell the point lies on (-1: lower half, +1: upper half)
-template <typename R> __device__ __forceinline__ void cell_coords(const DevVox<R>& vx, const Pos3<R>& X, int c[3], int side[3])
+// cell of a point
+template <typename R> __device__ __forceinline__ void cell_coords(const DevVox<R>& vx, const Pos3<R>& X, int c[3])
 {
-    R q[3] = {(X.x - vx.origin[0]) * vx.inv_cell, (X.y - vx.origin[1]) * vx.inv_cell, (X.z - vx.origin[2]) * vx.inv_cell};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        R fl = dev_floor<R>(q[k]);
-        c[k] = (int)fl;
-        side[k] = (q[k] - fl < R(0.5)) ? -1 : 1;
-    }
+    c[0] = (int)dev_floor<R>((X.x - vx.origin[0]) * vx.inv_cell);
+    c[1] = (int)dev_floor<R>((X.y - vx.origin[1]) * vx.inv_cell);
+    c[2] = (int)dev_floor<R>((X.z - vx.origin[2]) * vx.inv_cell);
 }
 
 // compact index of cell (cx, cy, cz), or -1 if the cell is not in the index
@@ -106,26 +102,25 @@ template <typename R> __device__ __forceinline__ int vox_index(const DevVox<R>& 
     return (int)e.y + __popc(e.x & ((1u << bit) - 1u));
 }
 
-// slot range [b, e) of the particles in cells (x0, y, z) and (x0 + 1, y, z).  Compact indices ascend along x
-// inside a row (also across its words), so the two cells' particles are contiguous in the sorted state whether or
-// not both are occupied.  Empty (b == e) outside the grid.
+// slot range [b, e) of the particles in cells (x0 - 1 .. x0 + 1, y, z).  Compact indices ascend along x inside a
+// row (also across its words), so the particles of the run are contiguous in the sorted state whichever of its
+// cells are occupied.  Every row ends with a spare word whose base is the row's end, so word (x >> 5) exists for
+// x = ncx.  Empty (b == e) outside the grid.
 template <typename R> __device__ __forceinline__ void row_range(const StepArgs<R>& a, int x0, int y, int z, int& b, int& e)
 {
     const DevVox<R>& vx = a.vox;
     b = e = 0;
-    if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz || (unsigned)x0 >= (unsigned)(vx.ncx - 1)) return;
-    const uint2* w = vx.words + ((size_t)z * vx.ncy + y) * vx.nwx + (x0 >> 5);
-    const uint2 e0 = __ldg(w);
-    const unsigned bit = x0 & 31;
-    int lo, hi;
-    if (bit != 31) {
-        const unsigned m2 = 0xffffffffu >> (30 - bit);   // bits 0 .. bit + 1
-        lo = (int)e0.y + __popc(e0.x & (m2 >> 2));
-        hi = (int)e0.y + __popc(e0.x & m2);
+    if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz || x0 < 1 || x0 > vx.ncx - 2) return;
+    const int xl = x0 - 1, xh = x0 + 2;   // ranks of xl and xh bound the run
+    const uint2* row = vx.words + ((size_t)z * vx.ncy + y) * vx.nwx;
+    const uint2 e0 = __ldg(row + (xl >> 5));
+    const int lo = (int)e0.y + __popc(e0.x & ((1u << (xl & 31)) - 1u));
+    int hi;
+    if ((xh >> 5) == (xl >> 5)) {
+        hi = (int)e0.y + __popc(e0.x & ((1u << (xh & 31)) - 1u));
     } else {   // the run straddles two words of the row
-        const uint2 e1 = __ldg(w + 1);
-        lo = (int)e0.y + __popc(e0.x & 0x7fffffffu);
-        hi = (int)e1.y + (int)(e1.x & 1u);
+        const uint2 e1 = __ldg(row + (xh >> 5));
+        hi = (int)e1.y + __popc(e1.x & ((1u << (xh & 31)) - 1u));
     }
     if (hi > lo) {
         b = a.start[lo];
@@ -143,8 +138,8 @@ template <typename R> __device__ __forceinline__ int resident_count(const StepAr
 template <typename R> __device__ __forceinline__ uint32_t bucket_key(const StepArgs<R>& a, const Pos3<R>& X, int vid, BlockCounters& bc)
 {
     if (a.mode == T2D_NEIGH_TABLE) return (uint32_t)vid;
-    int c[3], side[3];
-    cell_coords<R>(a.vox, X, c, side);
+    int c[3];
+    cell_coords<R>(a.vox, X, c);
     int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
     if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket, searched by everyone
         bc.cell_fb++;
@@ -401,9 +396,9 @@ __device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> 
 
 // ---------------------------------------------------------------------------------------------------
 // K3-K5 fused (Euclidean criterion).  d_ij = ||X_i - X_j|| on the 3-D positions of the previous projection.
-// Cell edge = 2*rmax: a neighbour within rmax lies in the particle's own cell or the adjacent one on the
-// nearer side per axis -> 2x2 rows of 2 x-adjacent cells; a row's 2 cells are ONE contiguous slot range of the
-// sorted state (row_range), so a particle walks 4 ranges (+ the overflow bucket, normally empty).
+// Cell edge = rmax: a neighbour within rmax lies in the 3 x 3 x 3 cells around the particle's own = 3 x 3 rows of
+// 3 x-adjacent cells; a row's 3 cells are ONE contiguous slot range of the sorted state (row_range), so a particle
+// walks at most 9 ranges (3.2 non-empty on average on a surface) + the overflow bucket, normally empty.
 // One thread per particle; the new state goes to `alt` (other particles still read `cur`), together with
 // the particle's next bucket key, arrival rank and the histogram for the counting sort that follows.
 //
@@ -417,7 +412,7 @@ __device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> 
 // ---------------------------------------------------------------------------------------------------
 constexpr int EUCLID_KMAX = 48;
 constexpr int STEP_THREADS = 128;
-constexpr int NRANGE = 5;
+constexpr int NRANGE = 10;   // 3 x 3 rows + the overflow bucket
 
 template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 4) k_step_euclid_exact(StepArgs<R> a)
 {
@@ -436,13 +431,12 @@ template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREAD
         const int heading = (int)Pi.w;
         int nr = 0;   // non-empty candidate ranges of this particle
         {
-            int c[3], side[3];
-            cell_coords<R>(a.vox, Pi, c, side);
-            const int x0 = side[0] < 0 ? c[0] - 1 : c[0];
+            int c[3];
+            cell_coords<R>(a.vox, Pi, c);
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < 9; ++m) {
                 int rb, re;
-                row_range<R>(a, x0, c[1] + ((m & 1) ? side[1] : 0), c[2] + ((m & 2) ? side[2] : 0), rb, re);
+                row_range<R>(a, c[0], c[1] + (m % 3) - 1, c[2] + (m / 3) - 1, rb, re);
                 if (re > rb) {
                     s_beg[nr][tid] = rb;
                     s_end[nr][tid] = re;
@@ -607,11 +601,37 @@ __device__ __forceinline__ int locate_face_contains(const DevMesh<float>& m, flo
 }
 
 struct FastSmem {
+    int rb[NRANGE][STEP_THREADS], rl[NRANGE][STEP_THREADS];   // candidate ranges (begin, length), longest first; column = thread
+    // particles that left their previous face: queue, point, located face
     float px[STEP_THREADS], py[STEP_THREADS];
     int face[STEP_THREADS];
     int queue[STEP_THREADS];
     int nq;
 };
+
+// accumulators of one particle's neighbour sums
+struct PairAcc {
+    float fx = 0.0f, fy = 0.0f;
+    double mx = 0.0, my = 0.0;
+    int nzero = 0;   // in-range candidates at distance 0 (the particle itself and coincident ones)
+};
+
+// one in-range pair.  F_ij / d = -k (2 sigma - d) / (2 sigma d) = (-k) / d + k / (2 sigma): one FMA on 1/d
+// (ForceHelper.cpp:84-104); d = 0 (the particle itself: ui - uj = 0, no force; or a coincident one) -> d := 0.001
+// (ForceHelper.cpp:59-62)
+__device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const Real2<float>* __restrict__ uv, int j, float d2,
+                                          const Real2<float>& ui, float g1, float g0, PairAcc& acc)
+{
+    const double2 t = cs[j];
+    const Real2<float> uj = uv[j];
+    acc.mx += t.x;
+    acc.my += t.y;
+    const bool zero = d2 == 0.0f;
+    acc.nzero += zero ? 1 : 0;
+    const float g = fmaf(rsqrtf(zero ? 1e-6f : d2), g1, g0);
+    acc.fx = fmaf(g, ui.x - uj.x, acc.fx);
+    acc.fy = fmaf(g, ui.y - uj.y, acc.fy);
+}
 
 template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step_euclid_fast(StepArgs<float> a)
 {
@@ -631,57 +651,81 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step
     bool need_locate = false;
     float fx = 0.0f, fy = 0.0f;
 
+    const float r2s = a.two_sigma * a.two_sigma, r2c = a.color_r * a.color_r;
+    const float g1 = -a.k, g0 = a.k / a.two_sigma;
+    const Pos3<R>* __restrict__ pos = a.cur.pos;
+    const double2* __restrict__ cs = a.cur.cs;
+    const Real2<R>* __restrict__ uv = a.cur.uv;
+    PairAcc acc;
+    int hits = 0;
+
     if (live) {
+        // candidate ranges: 3 x 3 rows of 3 x-adjacent cells (+ the overflow bucket, normally empty), sorted by
+        // length: every lane walks its longest range first, so the lanes of a warp finish their m-th range at about
+        // the same time (measured on the bench workload: 67 instead of 92 warp iterations per particle row)
         const Pos3<R> Pi = a.cur.pos[i];
-        const double2 own = a.cur.cs[i];
         ui = a.cur.uv[i];
-        int rb[4], re[4];
-        {
-            int c[3], side[3];
-            cell_coords<R>(a.vox, Pi, c, side);
-            const int x0 = side[0] < 0 ? c[0] - 1 : c[0];
+        int rb[9], rl[9];
+        int c[3];
+        cell_coords<R>(a.vox, Pi, c);
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
-                row_range<R>(a, x0, c[1] + ((m & 1) ? side[1] : 0), c[2] + ((m & 2) ? side[2] : 0), rb[m], re[m]);
+        for (int m = 0; m < 9; ++m) {
+            int e;
+            row_range<R>(a, c[0], c[1] + (m % 3) - 1, c[2] + (m / 3) - 1, rb[m], e);
+            rl[m] = e - rb[m];
         }
-        const int ob = a.start[a.vox.M], oe = a.start[a.vox.M + 1];   // overflow bucket: normally empty
-        const float r2s = a.two_sigma * a.two_sigma, r2c = a.color_r * a.color_r;
-        const float gk = -a.k / a.two_sigma;
-        double mx = 0.0, my = 0.0;
-        int nzero = 0;   // candidates at distance 0 (the particle itself and coincident ones): never coloured
-        const Pos3<R>* __restrict__ pos = a.cur.pos;
-        const double2* __restrict__ cs = a.cur.cs;
-        const Real2<R>* __restrict__ uv = a.cur.uv;
-        auto scan = [&](int jb, int je) {
-            for (int j = jb; j < je; ++j) {
-                const Pos3<R> Pj = pos[j];
+#define T2D_CSWAP(x, y)                                \
+    if (rl[x] < rl[y]) {                               \
+        int t_ = rl[x]; rl[x] = rl[y]; rl[y] = t_;     \
+        t_ = rb[x]; rb[x] = rb[y]; rb[y] = t_;         \
+    }
+        // 9-input sorting network (25 compare-exchanges)
+        T2D_CSWAP(0, 1) T2D_CSWAP(3, 4) T2D_CSWAP(6, 7) T2D_CSWAP(1, 2) T2D_CSWAP(4, 5) T2D_CSWAP(7, 8)
+        T2D_CSWAP(0, 1) T2D_CSWAP(3, 4) T2D_CSWAP(6, 7) T2D_CSWAP(0, 3) T2D_CSWAP(3, 6) T2D_CSWAP(0, 3)
+        T2D_CSWAP(1, 4) T2D_CSWAP(4, 7) T2D_CSWAP(1, 4) T2D_CSWAP(2, 5) T2D_CSWAP(5, 8) T2D_CSWAP(2, 5)
+        T2D_CSWAP(1, 3) T2D_CSWAP(5, 7) T2D_CSWAP(2, 6) T2D_CSWAP(4, 6) T2D_CSWAP(2, 4) T2D_CSWAP(2, 3)
+        T2D_CSWAP(5, 6)
+#undef T2D_CSWAP
+        int nr = 0;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+            sm.rb[m][tid] = rb[m];
+            sm.rl[m][tid] = rl[m];
+            nr += rl[m] > 0 ? 1 : 0;
+        }
+        {
+            const int ob = a.start[a.vox.M], ol = a.start[a.vox.M + 1] - ob;
+            if (ol > 0) {
+                sm.rb[nr][tid] = ob;
+                sm.rl[nr][tid] = ol;
+                nr++;
+            }
+        }
+#pragma unroll 1
+        for (int m = 0; m < nr; ++m) {
+            const int jb = sm.rb[m][tid], len = sm.rl[m][tid];
+            const Pos3<R>* q = pos + jb;
+            for (int t = 0; t < len; ++t) {
+                const Pos3<R> Pj = q[t];
                 const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
                 const float d2 = dx * dx + dy * dy + dz * dz;
                 color += (d2 <= r2c) ? 1 : 0;   // _2DTissue::count_particle_neighbors (distance-0 candidates removed below)
                 if (d2 < r2s) {
-                    const double2 t = cs[j];
-                    const Real2<R> uj = uv[j];
-                    mx += t.x;
-                    my += t.y;
-                    npairs++;
-                    float rinv = rsqrtf(d2), d = d2 * rinv;
-                    if (d2 == 0.0f) {   // itself (force term vanishes: ui - uj = 0) or a coincident particle: d := 0.001 (ForceHelper.cpp:59-62)
-                        d = 0.001f;
-                        rinv = 1000.0f;
-                        nzero++;
-                    }
-                    const float g = gk * (a.two_sigma - d) * rinv;   // F_ij / d
-                    fx += g * (ui.x - uj.x);
-                    fy += g * (ui.y - uj.y);
+                    pair_term(cs, uv, jb + t, d2, ui, g1, g0, acc);
+                    hits++;
                 }
             }
-        };
-#pragma unroll
-        for (int m = 0; m < 4; ++m) scan(rb[m], re[m]);
-        if (oe > ob) scan(ob, oe);
+        }
+    }
+
+    if (live) {
+        const double2 own = a.cur.cs[i];
+        fx = acc.fx;
+        fy = acc.fy;
+        const double mx = acc.mx, my = acc.my;
         if (r2s > 0.0f) {
-            color -= nzero;
-            npairs -= 1;   // itself
+            color -= acc.nzero;
+            npairs = (unsigned)(hits - 1);   // itself
         } else {
             color -= 1;
         }
@@ -766,8 +810,8 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step
             a.alt.color[i] = color;
             a.alt.cs[i] = ncs;
             if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
-                int c[3], side[3];
-                cell_coords<R>(a.vox, X, c, side);
+                int c[3];
+                cell_coords<R>(a.vox, X, c);
                 int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
                 if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket
                     atomicAdd(&a.counters->cell_fallbacks, 1ull);
