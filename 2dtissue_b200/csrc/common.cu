@@ -6,10 +6,13 @@ namespace t2d {
 // ---------------------------------------------------------------------------------------------------
 // exclusive scan of count[0..M) into start[0..M], zeroing count for the next step.
 // Three launches: per-tile sums -> scan of the tile sums (one block) -> per-tile scan + offset.
-// A tile is 1024 threads x 4 ints (16-byte loads).  M is padded to a multiple of 4 by the allocator.
+// A tile is 256 threads x 16 ints (four 16-byte loads per thread, all issued before the first use: the kernels
+// are pure streaming, so memory-level parallelism per thread is what reaches HBM bandwidth).
+// The allocator pads count/start to a multiple of 4 ints.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_TILE = SCAN_THREADS * 4;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_VEC = 4;                           // int4 loads per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_VEC * 4;
 
 int scan_blocks(int M) { return (M + SCAN_TILE - 1) / SCAN_TILE; }
 
@@ -44,28 +47,41 @@ __device__ __forceinline__ int block_incl_scan(int v, int* total)
     return inc + base;
 }
 
+// this thread's SCAN_VEC int4 of the tile (vector v covers ints [base + (v * SCAN_THREADS + tid) * 4, +4)): coalesced
+__device__ __forceinline__ void tile_load(const int* __restrict__ count, int M, int tile, int4 q[SCAN_VEC])
+{
+#pragma unroll
+    for (int v = 0; v < SCAN_VEC; ++v) {
+        const int base = tile * SCAN_TILE + (v * SCAN_THREADS + threadIdx.x) * 4;
+        if (base + 3 < M) {
+            q[v] = *reinterpret_cast<const int4*>(count + base);
+        } else {
+            int t[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k)
+                if (base + k < M) t[k] = count[base + k];
+            q[v] = make_int4(t[0], t[1], t[2], t[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const int* __restrict__ count, int* __restrict__ sums, int M)
 {
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    int4 q[SCAN_VEC];
+    tile_load(count, M, blockIdx.x, q);
     int v = 0;
-    if (base + 3 < M) {
-        int4 q = *reinterpret_cast<const int4*>(count + base);
-        v = q.x + q.y + q.z + q.w;
-    } else {
-        for (int k = 0; k < 4; ++k)
-            if (base + k < M) v += count[base + k];
-    }
+#pragma unroll
+    for (int k = 0; k < SCAN_VEC; ++k) v += q[k].x + q[k].y + q[k].z + q[k].w;
     int total;
     block_incl_scan(v, &total);
     if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(int* sums, int nb)
+__global__ void __launch_bounds__(1024) k_scan_sums(int* sums, int nb)
 {
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
         int i = b0 + threadIdx.x;
         int v = (i < nb) ? sums[i] : 0;
         int total;
@@ -82,37 +98,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(int* sums, int nb)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int* __restrict__ count, int* __restrict__ start,
                                                              const int* __restrict__ sums, int M, int nb)
 {
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
-    int q[4] = {0, 0, 0, 0};
-    if (base + 3 < M) {
-        int4 t = *reinterpret_cast<const int4*>(count + base);
-        q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
-        *reinterpret_cast<int4*>(count + base) = make_int4(0, 0, 0, 0);
-    } else {
-        for (int k = 0; k < 4; ++k)
-            if (base + k < M) {
-                q[k] = count[base + k];
-                count[base + k] = 0;
-            }
-    }
-    int v = q[0] + q[1] + q[2] + q[3];
-    int total;
-    int inc = block_incl_scan(v, &total);
-    int off = sums[blockIdx.x] + inc - v;
-    if (base + 3 < M) {
+    int4 q[SCAN_VEC];
+    tile_load(count, M, blockIdx.x, q);
+    // vector v of the tile is scanned as a row of SCAN_THREADS * 4 ints; rows are chained through `carry`
+    int carry = sums[blockIdx.x];
+#pragma unroll
+    for (int v = 0; v < SCAN_VEC; ++v) {
+        const int base = blockIdx.x * SCAN_TILE + (v * SCAN_THREADS + threadIdx.x) * 4;
+        const int s = q[v].x + q[v].y + q[v].z + q[v].w;
+        int total;
+        const int inc = block_incl_scan(s, &total);
         int4 o;
-        o.x = off;
-        o.y = off + q[0];
-        o.z = o.y + q[1];
-        o.w = o.z + q[2];
-        *reinterpret_cast<int4*>(start + base) = o;
-    } else {
-        int r = off;
-        for (int k = 0; k < 4; ++k)
-            if (base + k < M) {
-                start[base + k] = r;
-                r += q[k];
-            }
+        o.x = carry + inc - s;
+        o.y = o.x + q[v].x;
+        o.z = o.y + q[v].y;
+        o.w = o.z + q[v].z;
+        if (base + 3 < M) {
+            *reinterpret_cast<int4*>(start + base) = o;
+            *reinterpret_cast<int4*>(count + base) = make_int4(0, 0, 0, 0);
+        } else {
+            const int t[4] = {o.x, o.y, o.z, o.w};
+            for (int k = 0; k < 4; ++k)
+                if (base + k < M) {
+                    start[base + k] = t[k];
+                    count[base + k] = 0;
+                }
+        }
+        carry += total;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) start[M] = sums[nb];
 }
@@ -121,7 +133,7 @@ void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s)
 {
     const int nb = scan_blocks(M);
     k_scan_tile_sums<<<nb, SCAN_THREADS, 0, s>>>(count, blocksums, M);
-    k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(blocksums, nb);
+    k_scan_sums<<<1, 1024, 0, s>>>(blocksums, nb);
     k_scan_apply<<<nb, SCAN_THREADS, 0, s>>>(count, start, blocksums, M, nb);
 }
 

@@ -411,7 +411,10 @@ __device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> 
 //                        their previous face.
 // ---------------------------------------------------------------------------------------------------
 constexpr int EUCLID_KMAX = 48;
-constexpr int STEP_THREADS = 128;
+#ifndef T2D_STEP_THREADS
+#define T2D_STEP_THREADS 128
+#endif
+constexpr int STEP_THREADS = T2D_STEP_THREADS;
 constexpr int NRANGE = 10;   // 3 x 3 rows + the overflow bucket
 
 template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 4) k_step_euclid_exact(StepArgs<R> a)
@@ -602,23 +605,17 @@ __device__ __forceinline__ int locate_face_contains(const DevMesh<float>& m, flo
 
 struct FastSmem {
     int rb[NRANGE][STEP_THREADS], rl[NRANGE][STEP_THREADS];   // candidate ranges (begin, length), longest first; column = thread
-    // particles that left their previous face: queue, point, located face
-    float px[STEP_THREADS], py[STEP_THREADS];
-    int face[STEP_THREADS];
-    int queue[STEP_THREADS];
-    int nq;
 };
 
 // accumulators of one particle's neighbour sums
 struct PairAcc {
     float fx = 0.0f, fy = 0.0f;
     double mx = 0.0, my = 0.0;
-    int nzero = 0;   // in-range candidates at distance 0 (the particle itself and coincident ones)
 };
 
 // one in-range pair.  F_ij / d = -k (2 sigma - d) / (2 sigma d) = (-k) / d + k / (2 sigma): one FMA on 1/d
-// (ForceHelper.cpp:84-104); d = 0 (the particle itself: ui - uj = 0, no force; or a coincident one) -> d := 0.001
-// (ForceHelper.cpp:59-62)
+// (ForceHelper.cpp:84-104).  d = 0 is the particle itself or one coincident with it (ForceHelper.cpp:59-62 sets
+// d := 0.001): ui - uj = 0 there, so the term vanishes for any finite 1/d — the clamp only keeps it finite.
 __device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const Real2<float>* __restrict__ uv, int j, float d2,
                                           const Real2<float>& ui, float g1, float g0, PairAcc& acc)
 {
@@ -626,20 +623,25 @@ __device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const 
     const Real2<float> uj = uv[j];
     acc.mx += t.x;
     acc.my += t.y;
-    const bool zero = d2 == 0.0f;
-    acc.nzero += zero ? 1 : 0;
-    const float g = fmaf(rsqrtf(zero ? 1e-6f : d2), g1, g0);
+    const float g = fmaf(rsqrtf(fmaxf(d2, 1e-36f)), g1, g0);
     acc.fx = fmaf(g, ui.x - uj.x, acc.fx);
     acc.fy = fmaf(g, ui.y - uj.y, acc.fy);
 }
 
-template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step_euclid_fast(StepArgs<float> a)
+#ifndef T2D_UNROLL
+#define T2D_UNROLL 4
+#endif
+constexpr int FAST_UNROLL = T2D_UNROLL;   // candidates per trip of the inner loop (loads of a trip are issued together)
+#ifndef T2D_FAST_MIN_BLOCKS
+#define T2D_FAST_MIN_BLOCKS 8
+#endif
+
+template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_MIN_BLOCKS) k_step_euclid_fast(StepArgs<float> a)
 {
     typedef float R;
     __shared__ FastSmem sm;
     const int tid = threadIdx.x;
     const int i = blockIdx.x * STEP_THREADS + tid;
-    if (MOVING && tid == 0) sm.nq = 0;
     const bool resident = i < resident_count<R>(a);
     const int4 ai = resident ? a.cur.aux[i] : make_int4(0, 0, 0, ORIGIN_DEAD);
     const bool live = resident && ai.w >= 0;   // slab mode: halo copies are read by others, never advanced
@@ -656,6 +658,7 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step
     const Pos3<R>* __restrict__ pos = a.cur.pos;
     const double2* __restrict__ cs = a.cur.cs;
     const Real2<R>* __restrict__ uv = a.cur.uv;
+    const unsigned r2c_bits = __float_as_uint(r2c);
     PairAcc acc;
     int hits = 0;
 
@@ -692,6 +695,13 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step
             sm.rb[m][tid] = rb[m];
             sm.rl[m][tid] = rl[m];
             nr += rl[m] > 0 ? 1 : 0;
+#ifdef T2D_PREFETCH
+            if (m > 0 && m < T2D_PREFETCH && rl[m] > 0) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pos + rb[m]));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(cs + rb[m]));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(uv + rb[m]));
+            }
+#endif
         }
         {
             const int ob = a.start[a.vox.M], ol = a.start[a.vox.M + 1] - ob;
@@ -705,11 +715,14 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step
         for (int m = 0; m < nr; ++m) {
             const int jb = sm.rb[m][tid], len = sm.rl[m][tid];
             const Pos3<R>* q = pos + jb;
+#pragma unroll FAST_UNROLL
             for (int t = 0; t < len; ++t) {
                 const Pos3<R> Pj = q[t];
                 const float dx = Pi.x - Pj.x, dy = Pi.y - Pj.y, dz = Pi.z - Pj.z;
                 const float d2 = dx * dx + dy * dy + dz * dz;
-                color += (d2 <= r2c) ? 1 : 0;   // _2DTissue::count_particle_neighbors (distance-0 candidates removed below)
+                // _2DTissue::count_particle_neighbors: 0 != d <= 2.4 sigma, as ONE unsigned compare on the bit patterns
+                // (d2 >= 0: bits(d2) - 1 wraps to 0xffffffff for d2 == 0 and keeps the order of positive floats)
+                color += (__float_as_uint(d2) - 1u < r2c_bits) ? 1 : 0;
                 if (d2 < r2s) {
                     pair_term(cs, uv, jb + t, d2, ui, g1, g0, acc);
                     hits++;
@@ -723,12 +736,7 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step
         fx = acc.fx;
         fy = acc.fy;
         const double mx = acc.mx, my = acc.my;
-        if (r2s > 0.0f) {
-            color -= acc.nzero;
-            npairs = (unsigned)(hits - 1);   // itself
-        } else {
-            color -= 1;
-        }
+        npairs = hits > 0 ? (unsigned)(hits - 1) : 0u;   // without itself
 
         // speed and velocity (Locomotion.cpp:71-81): own heading's unit vector from the cs array
         const float absF = sqrtf(fx * fx + fy * fy) + a.v0;
@@ -768,24 +776,11 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, 8) k_step
     }
 
     if (MOVING) {
-        // the particles that left their previous face are located by the first threads of the CTA, densely packed
-        __syncthreads();   // sm.nq = 0 visible
-        if (need_locate) {
-            const int q = atomicAdd(&sm.nq, 1);
-            sm.queue[q] = tid;
-            sm.px[tid] = p.x;
-            sm.py[tid] = p.y;
-        }
-        __syncthreads();
-        if (tid < sm.nq) {
-            const int o = sm.queue[tid];
-            sm.face[o] = locate_face_contains(a.mesh, sm.px[o], sm.py[o]);
-        }
-        __syncthreads();
         if (live) {
             int f = hint;
             if (need_locate) {
-                f = sm.face[tid];
+                // the particle left its previous face (about 1 in 7 per step): first face of its grid cell that contains it
+                f = locate_face_contains(a.mesh, p.x, p.y);
                 if (f < 0) {   // within rounding of an edge (or outside every listed face): the reference's arg-min over distances
                     BlockCounters lc;
                     f = locate_face<R>(a.mesh, p.x, p.y, lc);
