@@ -103,8 +103,13 @@ def workload_spec(args, world):
     w = args.workload
     if w == "c4shard":
         per = args.particles_per_gpu or 2_000_000
-        return dict(name="c4shard: %d particles/GPU, refined ellipsoid chart (2 levels), Euclidean cutoff" % per,
-                    per_gpu=per, total=per * world, mode="euclid", refine=2, dtype=args.dtype or "f32")
+        # "high-resolution ellipsoid mesh": the chart is refined with the particle count so that the particles per
+        # face stay at 7-13 (2M on 149k faces ... 16M on 2.4M faces).  With a fixed mesh the reference's own physics
+        # (distance-weighted lift + 1/d force) blows up as soon as ~25 particles share a face: 4M particles on the
+        # 149k-face chart lose particles after ~10 steps on ONE GPU too (Validation.cpp:66-72 would throw).
+        refine = 2 + (0 if world <= 1 else (1 if world <= 4 else 2))
+        return dict(name="c4shard: %d particles/GPU, ellipsoid chart refined %d levels, Euclidean cutoff" % (per, refine),
+                    per_gpu=per, total=per * world, mode="euclid", refine=refine, dtype=args.dtype or "f32")
     if w == "c2":
         return dict(name="c2: 10k particles, ellipsoid_x4 chart, Euclidean cutoff", per_gpu=10_000, total=10_000 * world,
                     mode="euclid", refine=0, dtype=args.dtype or "f32")
@@ -265,9 +270,15 @@ def main_ours(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.counters()["kernel_launches"]
+    if fault:
+        sys.stderr.write("rank %d: simulation fault mask %d during the timed steps (1 lost, 2 non-finite, 4 wrap cap, "
+                         "8 migration, 16 message overflow): the measurement is invalid\n" % (rank, fault))
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tf = torch.tensor([(fault >> b) & 1 for b in range(8)], dtype=torch.int32, device="cuda")   # OR over ranks, bit by bit
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fault = sum(int(v) << b for b, v in enumerate(tf.tolist()))
     dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
     value = spec["total"] * args.steps / (dev_ms * 1e-3)
