@@ -24,7 +24,7 @@ int nccl_unique_id(uint8_t* out, std::string* err);
 NcclLink* nccl_link_create(int rank, int world, const uint8_t* id_bytes, std::string* err);
 void nccl_link_destroy(NcclLink* l);
 int nccl_exchange(NcclLink* l, const void* send_left, void* recv_left, const void* send_right, void* recv_right, size_t bytes,
-                  cudaStream_t s, std::string* err);
+                  const void* far_send, void* far_recv, size_t far_bytes, cudaStream_t s, std::string* err);
 }
 
 using namespace t2d;
@@ -90,7 +90,7 @@ struct EngineBase {
     virtual int hop_table(uint8_t* out) = 0;
     virtual int profile_step(const char** names, double* ms, int cap) = 0;
     // slab mode
-    virtual int comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* left, EngineBase* right) = 0;
+    virtual int comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* const* group) = 0;
     virtual int comm_destroy() = 0;
     virtual void comm_phase1() = 0;                 // (advance +) classify + pack into the send buffers
     virtual void comm_local_send() = 0;             // local group: copy the messages into the neighbours' receive buffers
@@ -99,6 +99,7 @@ struct EngineBase {
     virtual int owned_count() = 0;
     virtual int download_ids(uint32_t* ids) = 0;
     virtual unsigned char* comm_recv_buffer(int dir) = 0;
+    virtual unsigned char* comm_far_slot(int src) = 0;   // where rank `src`'s far message lands in this context
     virtual cudaEvent_t comm_event(int which) = 0;   // 0: messages sent, 1: messages consumed
     virtual bool comm_is_local() const = 0;
     virtual bool halo_ready() const = 0;
@@ -148,7 +149,7 @@ template <typename R> class Engine : public EngineBase {
     int forces(double* F, int* new_heading, int* color) override;
     int hop_table(uint8_t* out) override;
     int profile_step(const char** names, double* ms, int cap) override;
-    int comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* left, EngineBase* right) override;
+    int comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* const* group) override;
     int comm_destroy() override;
     void comm_phase1() override;
     void comm_local_send() override;
@@ -157,6 +158,7 @@ template <typename R> class Engine : public EngineBase {
     int owned_count() override;
     int download_ids(uint32_t* ids) override;
     unsigned char* comm_recv_buffer(int dir) override { return comm_recv_[dir].p; }
+    unsigned char* comm_far_slot(int src) override { return far_recv_.p + (size_t)src * far_bytes_; }
     cudaEvent_t comm_event(int which) override { return which == 0 ? ev_sent_ : ev_consumed_; }
     bool comm_is_local() const override { return comm_on_ && !link_; }
     bool halo_ready() const override { return halo_valid_; }
@@ -188,8 +190,9 @@ template <typename R> class Engine : public EngineBase {
     int resident_ = 0;   // resident slots (owned + halo) at the last compaction
     NcclLink* link_ = nullptr;
     EngineBase* peer_[2] = {nullptr, nullptr};
-    size_t msg_bytes_ = 0;
-    DevBuf<unsigned char> comm_send_[2], comm_recv_[2];
+    std::vector<EngineBase*> group_;   // local slab group: every rank's engine (far channel)
+    size_t msg_bytes_ = 0, far_bytes_ = 0;
+    DevBuf<unsigned char> comm_send_[2], comm_recv_[2], far_send_, far_recv_;
     DevBuf<DevCommState> comm_state_;
     DevBuf<int> d_cflag_, d_coff_, d_cblk_;
     cudaEvent_t ev_sent_ = nullptr, ev_consumed_ = nullptr;
@@ -778,11 +781,12 @@ template <typename R> int Engine<R>::download_ids(uint32_t* ids)
 
 // ---- slab mode -----------------------------------------------------------------------------------------
 template <typename R>
-int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* left, EngineBase* right)
+int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* const* group)
 {
     CK(cudaSetDevice(device_));
     if (P_.neigh_mode != T2D_NEIGH_EUCLID) throw CudaError{"slab mode supports the Euclidean criterion only"};
     if (world < 1 || rank < 0 || rank >= world) throw CudaError{"bad rank / world"};
+    if (world > T2D_MAX_WORLD) throw CudaError{"at most 16 slabs"};
     if (comm_on_) comm_destroy();
     for (int r = 0; r + 2 < world; ++r)
         if (!(cuts[r] < cuts[r + 1])) throw CudaError{"slab cuts must be ascending"};
@@ -813,6 +817,15 @@ int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* c
         A_.comm.send[d] = comm_send_[d].p;
         A_.comm.recv[d] = comm_recv_[d].p;
     }
+    for (int k = 0; k < world - 1; ++k) A_.comm.cuts[k] = (R)cuts_[k];
+    far_bytes_ = Launch<R>::comm_far_bytes();
+    far_send_.alloc(far_bytes_);
+    far_recv_.alloc(far_bytes_ * (size_t)world);
+    CK(cudaMemsetAsync(far_send_.p, 0, 16, stream_));
+    CK(cudaMemsetAsync(far_recv_.p, 0, far_bytes_ * (size_t)world, stream_));
+    A_.comm.far_send = far_send_.p;
+    A_.comm.far_recv = far_recv_.p;
+    A_.comm.far_bytes = far_bytes_;
     comm_state_.alloc(1);
     DevCommState st{this->N, this->N};
     CK(cudaMemcpyAsync(comm_state_.p, &st, sizeof(st), cudaMemcpyHostToDevice, stream_));
@@ -823,8 +836,13 @@ int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* c
     CK(cudaEventCreateWithFlags(&ev_sent_, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_consumed_, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(stream_));
-    peer_[0] = left;
-    peer_[1] = right;
+    group_.clear();
+    peer_[0] = peer_[1] = nullptr;
+    if (group) {
+        group_.assign(group, group + world);
+        peer_[0] = rank > 0 ? group[rank - 1] : nullptr;
+        peer_[1] = rank + 1 < world ? group[rank + 1] : nullptr;
+    }
     if (id) {
         std::string err;
         link_ = nccl_link_create(rank, world, id, &err);
@@ -857,6 +875,7 @@ template <typename R> void Engine<R>::comm_phase1()
 {
     CK(cudaSetDevice(device_));
     for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(comm_send_[d].p, 0, 16, stream_));
+    CK(cudaMemsetAsync(far_send_.p, 0, 16, stream_));
     prof_mark();
     if (halo_valid_) {
         A_.step = (uint64_t)step_index;
@@ -873,12 +892,16 @@ template <typename R> void Engine<R>::comm_phase1()
 template <typename R> void Engine<R>::comm_local_send()
 {
     CK(cudaSetDevice(device_));
+    const int me = A_.comm.rank, world = A_.comm.world;
+    for (int r = 0; r < world; ++r)
+        if (r != me) CK(cudaStreamWaitEvent(stream_, group_[r]->comm_event(1), 0));   // rank r has consumed the previous messages
     for (int d = 0; d < 2; ++d) {
         EngineBase* p = peer_[d];
         if (!p) continue;
-        CK(cudaStreamWaitEvent(stream_, p->comm_event(1), 0));   // the neighbour has consumed the previous message
         CK(cudaMemcpyPeerAsync(p->comm_recv_buffer(1 - d), p->device(), comm_send_[d].p, device_, msg_bytes_, stream_));
     }
+    for (int r = 0; r < world; ++r)
+        if (r != me) CK(cudaMemcpyPeerAsync(group_[r]->comm_far_slot(me), group_[r]->device(), far_send_.p, device_, far_bytes_, stream_));
     CK(cudaEventRecord(ev_sent_, stream_));
 }
 
@@ -887,13 +910,16 @@ template <typename R> void Engine<R>::comm_phase2()
     CK(cudaSetDevice(device_));
     if (link_) {
         std::string err;
-        if (nccl_exchange(link_, comm_send_[0].p, comm_recv_[0].p, comm_send_[1].p, comm_recv_[1].p, msg_bytes_, stream_, &err) != 0)
+        if (nccl_exchange(link_, comm_send_[0].p, comm_recv_[0].p, comm_send_[1].p, comm_recv_[1].p, msg_bytes_, far_send_.p,
+                          far_recv_.p, far_bytes_, stream_, &err) != 0)
             throw CudaError{err};
     } else {
-        for (int d = 0; d < 2; ++d)
-            if (peer_[d]) CK(cudaStreamWaitEvent(stream_, peer_[d]->comm_event(0), 0));
+        for (int r = 0; r < A_.comm.world; ++r)
+            if (r != A_.comm.rank) CK(cudaStreamWaitEvent(stream_, group_[r]->comm_event(0), 0));
     }
     Launch<R>::comm_unpack(A_, stream_);
+    Launch<R>::comm_unpack_far(A_, stream_);
+    if (A_.comm.world > 1) launches_++;
     prof_mark();
     launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
     prof_mark();
@@ -1362,14 +1388,15 @@ int t2d_comm_init(t2d_ctx* ctx, int rank, int world, const uint8_t id[T2D_UNIQUE
         ctx->err = "t2d_comm_init needs the NCCL unique id of rank 0 (t2d_comm_unique_id)";
         return -1;
     }
-    T2D_TRY(ctx, return ctx->eng->comm_init(rank, world, id, cuts, nullptr, nullptr);)
+    T2D_TRY(ctx, return ctx->eng->comm_init(rank, world, id, cuts, nullptr);)
 }
 int t2d_comm_init_local(t2d_ctx** ctxs, int world, const double* cuts)
 {
+    std::vector<EngineBase*> group;
+    for (int r = 0; r < world; ++r) group.push_back(ctxs[r]->eng.get());
     for (int r = 0; r < world; ++r) {
         t2d_ctx* c = ctxs[r];
-        T2D_TRY(c, c->eng->comm_init(r, world, nullptr, cuts, r > 0 ? ctxs[r - 1]->eng.get() : nullptr,
-                                     r + 1 < world ? ctxs[r + 1]->eng.get() : nullptr);)
+        T2D_TRY(c, c->eng->comm_init(r, world, nullptr, cuts, group.data());)
     }
     return 0;
 }

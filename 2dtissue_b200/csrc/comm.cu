@@ -113,10 +113,18 @@ void nccl_link_destroy(NcclLink* l)
 }
 
 // one message of `bytes` to each existing neighbour and one from each, in a single NCCL group on stream s
+// + the far message (far_bytes; far_recv has one slot per rank) to and from every other rank
 int nccl_exchange(NcclLink* l, const void* send_left, void* recv_left, const void* send_right, void* recv_right, size_t bytes,
-                  cudaStream_t s, std::string* err)
+                  const void* far_send, void* far_recv, size_t far_bytes, cudaStream_t s, std::string* err)
 {
     NCK(g_nccl.GroupStart());
+    if (l->world > 1 && far_bytes) {
+        for (int r = 0; r < l->world; ++r) {
+            if (r == l->rank) continue;
+            NCK(g_nccl.Send(far_send, far_bytes, ncclChar, r, l->comm, s));
+            NCK(g_nccl.Recv(static_cast<char*>(far_recv) + (size_t)r * far_bytes, far_bytes, ncclChar, r, l->comm, s));
+        }
+    }
     if (l->rank > 0) {
         NCK(g_nccl.Send(send_left, bytes, ncclChar, l->rank - 1, l->comm, s));
         NCK(g_nccl.Recv(recv_left, bytes, ncclChar, l->rank - 1, l->comm, s));

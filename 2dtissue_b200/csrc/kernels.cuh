@@ -1077,9 +1077,28 @@ template <typename R> __global__ void __launch_bounds__(256) k_comm_pack(StepArg
             const Pos3<R> P = a.cur.pos[i];
             const R x = P.x;
             bool keep = true;
-            if (x < cm.lo || x >= cm.hi) {
+            if (x < cm.lo - cm.halo || x >= cm.hi + cm.halo) {
+                // landed beyond the halo strip of an adjacent slab (seam re-entry / a very fast particle): the far
+                // channel — every rank sees it, so whoever has it in ITS halo strip gets a copy too; no halo copy here
+                int dest = 0;
+                for (int k = 0; k < cm.world - 1; ++k) dest += (x >= cm.cuts[k]) ? 1 : 0;
+                const int slot = atomicAdd(&msg_header<R>(cm.far_send)->n_mig, 1);
+                if (slot < FAR_CAP) {
+                    MigRec<R> r;
+                    r.pos = P;
+                    r.uv = a.cur.uv[i];
+                    r.rdot = a.cur.rdot[i];
+                    r.aux = make_int4(ax.x, ax.y, ax.z, 0);
+                    r.color = a.cur.color[i];
+                    r.pad[0] = dest;
+                    r.pad[1] = r.pad[2] = 0;
+                    msg_mig<R>(cm.far_send)[slot] = r;
+                } else {
+                    bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+                }
+                keep = false;
+            } else if (x < cm.lo || x >= cm.hi) {
                 const int dir = x < cm.lo ? 0 : 1;
-                if (x < cm.lo2 || x >= cm.hi2) bc.fault |= T2D_FAULT_MIGRATION;
                 const int slot = atomicAdd(&msg_header<R>(cm.send[dir])->n_mig, 1);
                 if (slot < cm.mig_cap) {
                     MigRec<R> r;
@@ -1188,6 +1207,51 @@ template <typename R> __global__ void __launch_bounds__(256) k_comm_unpack(StepA
         const uint32_t key = bucket_key<R>(a, P, vid, bc);
         a.key[slot] = key;
         a.rank[slot] = (uint32_t)atomicAdd(&a.count[key], 1);
+    }
+    flush_counters(bc, a.counters);
+}
+
+// the far channel: every rank sees every rank's far migrants; the destination slab adopts the particle, a rank whose halo
+// zone it landed in takes a halo copy.  Appended behind what k_comm_unpack appended (atomic cursor: the order inside a
+// bucket is arrival order everywhere in this library; the exact path sums by global id).
+template <typename R> __global__ void __launch_bounds__(256) k_comm_unpack_far(StepArgs<R> a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, src = blockIdx.y;
+    BlockCounters bc;
+    const DevComm<R>& cm = a.comm;
+    if (src != cm.rank) {
+        unsigned char* m = const_cast<unsigned char*>(cm.far_recv) + (size_t)src * cm.far_bytes;
+        const int n = min(msg_header<R>(m)->n_mig, FAR_CAP);
+        if (t < n) {
+            const MigRec<R> r = msg_mig<R>(m)[t];
+            const R x = r.pos.x;
+            const bool mine = r.pad[0] == cm.rank;
+            const bool halo = !mine && x >= cm.lo - cm.halo && x < cm.hi + cm.halo;
+            if (mine || halo) {
+                const int slot = atomicAdd(&cm.state->n_res, 1);
+                if (slot >= cm.capacity) {
+                    atomicSub(&cm.state->n_res, 1);
+                    bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+                } else {
+                    a.cur.pos[slot] = r.pos;
+                    a.cur.uv[slot] = r.uv;
+                    if (mine) {
+                        a.cur.rdot[slot] = r.rdot;
+                        a.cur.aux[slot] = r.aux;
+                        a.cur.color[slot] = r.color;
+                    } else {
+                        Real2<R> z = {R(0), R(0)};
+                        a.cur.rdot[slot] = z;
+                        a.cur.aux[slot] = make_int4(0, -1, r.aux.z, ORIGIN_GHOST);
+                        a.cur.color[slot] = 0;
+                    }
+                    if (a.cur.cs) a.cur.cs[slot] = trig_lookup(a.trig_d, (int)r.pos.w, bc.trig_fb);
+                    const uint32_t key = bucket_key<R>(a, r.pos, r.aux.x, bc);
+                    a.key[slot] = key;
+                    a.rank[slot] = (uint32_t)atomicAdd(&a.count[key], 1);
+                }
+            }
+        }
     }
     flush_counters(bc, a.counters);
 }
@@ -1325,6 +1389,11 @@ template <typename R> void Launch<R>::comm_unpack(const StepArgs<R>& a, cudaStre
     const int n = a.comm.mig_cap > a.comm.ghost_cap ? a.comm.mig_cap : a.comm.ghost_cap;
     k_comm_unpack<R><<<div_up(n, 256), 256, 0, s>>>(a);
 }
+template <typename R> void Launch<R>::comm_unpack_far(const StepArgs<R>& a, cudaStream_t s)
+{
+    if (a.comm.world > 1) k_comm_unpack_far<R><<<dim3(div_up(FAR_CAP, 256), a.comm.world), 256, 0, s>>>(a);
+}
+template <typename R> size_t Launch<R>::comm_far_bytes() { return 16 + (size_t)FAR_CAP * sizeof(MigRec<R>); }
 template <typename R> size_t Launch<R>::comm_message_bytes(int mig_cap, int ghost_cap)
 {
     return 16 + (size_t)mig_cap * sizeof(MigRec<R>) + (size_t)ghost_cap * sizeof(GhostRec<R>);

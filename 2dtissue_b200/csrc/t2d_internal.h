@@ -83,6 +83,9 @@ template <typename R> struct alignas(16) MigRec {     // full state of a particl
 struct CommHeader { int n_mig, n_ghost, pad0, pad1; };   // first 16 bytes of every message
 struct DevCommState { int n, n_res; };                   // sorted residents in `cur`; residents after the unpack
 
+constexpr int T2D_MAX_WORLD = 16;   // slabs per job (one box)
+constexpr int FAR_CAP = 1024;       // particles per step and rank that may leave for a NON-adjacent slab
+
 template <typename R> struct DevComm {
     int on = 0;
     int rank = 0, world = 1;
@@ -93,6 +96,13 @@ template <typename R> struct DevComm {
     unsigned char* send[2] = {nullptr, nullptr};         // 0: to rank-1, 1: to rank+1
     const unsigned char* recv[2] = {nullptr, nullptr};   // 0: from rank-1, 1: from rank+1
     DevCommState* state = nullptr;
+    // far channel: seam re-entry and the rare very fast particle can land anywhere on the surface (the reference's
+    // re-entry is not continuous in 3-D), so a particle that leaves for a non-adjacent slab goes into one small
+    // message that EVERY rank receives; the new owner adopts it, a rank whose halo zone it lands in takes a halo copy
+    R cuts[T2D_MAX_WORLD - 1] = {};             // slab k owns [cuts[k-1], cuts[k])
+    unsigned char* far_send = nullptr;           // CommHeader + MigRec[FAR_CAP] (pad[0] = destination slab)
+    const unsigned char* far_recv = nullptr;     // `world` slots of far_bytes each; slot r = what rank r sent
+    size_t far_bytes = 0;
 };
 
 struct DevCounters {   // mirrors t2d_counters' device-updated fields
@@ -145,6 +155,8 @@ template <typename R> struct Launch {
     static void project_only(const StepArgs<R>& a, cudaStream_t s);             // initial projection (get_r3d)
     static void comm_pack(const StepArgs<R>& a, cudaStream_t s);                // slabs: classify, pack migrants + halo, keys
     static void comm_unpack(const StepArgs<R>& a, cudaStream_t s);              // slabs: append received particles, keys
+    static void comm_unpack_far(const StepArgs<R>& a, cudaStream_t s);          // slabs: the far channel (all ranks' messages)
+    static size_t comm_far_bytes();
     static size_t comm_message_bytes(int mig_cap, int ghost_cap);
     static void tiling_only(const StepArgs<R>& a, Real2<R>* uv_old, Real2<R>* uv, int* heading, int N, cudaStream_t s);
     static void unit_vectors(const StepArgs<R>& a, const int* heading, R* out, int N, cudaStream_t s);

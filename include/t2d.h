@@ -60,7 +60,7 @@ enum { T2D_NEIGH_TABLE = 0, T2D_NEIGH_EUCLID = 1 };
 enum { T2D_PRECISION_FP64 = 0, T2D_PRECISION_FP32 = 1 };
 enum {
     T2D_FAULT_LOST = 1, T2D_FAULT_NONFINITE = 2, T2D_FAULT_WRAP_CAP = 4,
-    T2D_FAULT_MIGRATION = 8,      /* multi-GPU: a particle moved beyond the adjacent slab in one step */
+    T2D_FAULT_MIGRATION = 8,      /* reserved (particles that land beyond an adjacent halo strip travel through the far channel) */
     T2D_FAULT_COMM_OVERFLOW = 16  /* multi-GPU: a halo/migration message or the context's capacity overflowed */
 };
 

@@ -86,3 +86,36 @@ def test_slab_observables_and_counts(t2d, chart):
     c1.set_state(ref["uv"], ref["n"], ref["vid"], ref["r3d"])
     assert abs(phi - np.hypot(*[np.sum(f(np.deg2rad(ref["n"].astype(np.float64)))) for f in (np.cos, np.sin)]) / N) < 1e-12
     grp.close()
+
+
+def test_far_migration_is_exact(t2d, chart):
+    """Seam re-entry (and the rare very fast particle) is not continuous in 3-D under the reference's lift: a particle
+    can land several slabs away in ONE step.  Such particles travel through the far channel (every rank receives every
+    rank's far migrants); with 8 slabs the run must still equal the single-context run bit for bit."""
+    N, steps, world = 8000, 4, 8
+    uv, n = t2d.seed_particles(N, seed=1234)
+    sigma = float(np.sqrt(0.5 * 451.3 / (np.pi * N)))
+    # v0 = 700: 0.7 chart widths per step — every particle re-enters through the seam and lands somewhere else
+    kw = dict(v0=700.0, k=1.0, sigma=sigma, step_size=0.001, eta=0.02, seed=7, neigh_mode=t2d.NEIGH_EUCLID,
+              precision=t2d.PRECISION_FP64)
+    c0 = t2d.Context(chart, capacity=N, **kw)
+    c0.set_particles(uv, n)
+    s0 = c0.download(("uv", "n", "vid", "r3d"))
+    cuts = t2d.slab_cuts(s0["r3d"][:N], world)
+    grp = t2d.LocalSlabGroup(chart, world, cuts, capacity=N, **kw)
+    grp.set_state(s0)
+    prev, far = s0, 0
+    for s in range(steps):
+        assert c0.step(1) == 0
+        ref = c0.download()
+        assert grp.step(1) == 0, "no migration / overflow fault"
+        out, owned = grp.download()
+        assert sum(owned) == N
+        for k in ("n", "vid", "face", "color", "uv", "rdot", "r3d"):
+            assert np.array_equal(out[k], ref[k]), (s, k)
+        far += int(np.sum(np.abs(t2d.slab_of(ref["r3d"][:N], cuts) - t2d.slab_of(prev["r3d"][:N], cuts)) >= 2))
+        prev = ref
+    print("particles that jumped >= 2 slabs in one step: %d" % far)
+    assert far > 0, "the configuration no longer exercises the far channel"
+    grp.close()
+    c0.close()
