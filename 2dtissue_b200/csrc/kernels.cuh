@@ -1077,9 +1077,10 @@ template <typename R> __global__ void __launch_bounds__(256) k_comm_pack(StepArg
             const Pos3<R> P = a.cur.pos[i];
             const R x = P.x;
             bool keep = true;
-            if (x < cm.lo - cm.halo || x >= cm.hi + cm.halo) {
-                // landed beyond the halo strip of an adjacent slab (seam re-entry / a very fast particle): the far
-                // channel — every rank sees it, so whoever has it in ITS halo strip gets a copy too; no halo copy here
+            if (x < cm.lo2 + cm.halo || x >= cm.hi2 - cm.halo) {
+                // landed beyond the adjacent slab, or inside it but within r_max of ITS other cut (seam re-entry / a very
+                // fast particle): the far channel — every rank sees it, so the owner adopts it and whoever has it in its
+                // halo strip takes a copy; no halo copy here (slabs are at least 4 r_max wide)
                 int dest = 0;
                 for (int k = 0; k < cm.world - 1; ++k) dest += (x >= cm.cuts[k]) ? 1 : 0;
                 const int slot = atomicAdd(&msg_header<R>(cm.far_send)->n_mig, 1);
