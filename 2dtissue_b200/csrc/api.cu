@@ -186,7 +186,7 @@ template <typename R> class Engine : public EngineBase {
     int capacity_ = 0;
     bool sorted_ = false;   // `cur` is in bucket order and start[] is valid
     // slab mode
-    bool comm_on_ = false, halo_valid_ = false;
+    bool comm_on_ = false, halo_valid_ = false, closing_ = false;
     int resident_ = 0;   // resident slots (owned + halo) at the last compaction
     NcclLink* link_ = nullptr;
     EngineBase* peer_[2] = {nullptr, nullptr};
@@ -204,6 +204,7 @@ template <typename R> class Engine : public EngineBase {
         if (prof_ev_) cudaEventRecord(prof_ev_[(*prof_nev_)++], stream_);
     }
     double vox_sigma_ = -1, vox_color_ = -1;
+    double vox_xlo_ = -1e300, vox_xhi_ = 1e300;   // slab mode: only cells that overlap this x range are indexed
     int64_t launches_ = 0, steps_ = 0;
 
     // chart
@@ -320,6 +321,7 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
 
 template <typename R> Engine<R>::~Engine()
 {
+    closing_ = true;
     comm_destroy();
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -540,6 +542,26 @@ template <typename R> void Engine<R>::build_vox()
     CK(cudaMemcpyAsync(occ.data(), d_occ.p, nwords * sizeof(unsigned), cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     CK(cudaGetLastError());
+
+    // slab mode: a rank only ever holds particles of its slab and its halo strips, so cells outside that x range are
+    // dropped from the index — the bucket arrays (histogram, scan) then scale with the rank's particles, not the job's
+    if (vox_xlo_ > -1e299 || vox_xhi_ < 1e299) {
+        const int cx_lo = (int)std::max(0.0, std::floor((vox_xlo_ - org[0]) / cs)), cx_hi = (int)std::min((double)nc[0] - 1, std::floor((vox_xhi_ - org[0]) / cs));
+        for (size_t r = 0; r < nrows; ++r)
+            for (int w = 0; w < nwx; ++w) {
+                unsigned& bits = occ[r * nwx + w];
+                if (!bits) continue;
+                const int c0 = w * 32;
+                if (c0 + 31 < cx_lo || c0 > cx_hi) {
+                    bits = 0;
+                } else {
+                    unsigned keep = 0xffffffffu;
+                    if (cx_lo > c0) keep &= 0xffffffffu << (cx_lo - c0);
+                    if (cx_hi < c0 + 31) keep &= 0xffffffffu >> (c0 + 31 - cx_hi);
+                    bits &= keep;
+                }
+            }
+    }
 
     // non-empty rows in Morton order over (y, z) -> compact base index of every word
     auto spread = [](uint64_t v) {   // 32 bits -> every second bit
@@ -818,6 +840,10 @@ int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* c
         A_.comm.recv[d] = comm_recv_[d].p;
     }
     for (int k = 0; k < world - 1; ++k) A_.comm.cuts[k] = (R)cuts_[k];
+    // index only the cells this rank can hold: its slab + halo strips (+ one more r_max for rounding and cell edges)
+    vox_xlo_ = rank > 0 ? cut(rank - 1) - 3.0 * rmax : -1e300;
+    vox_xhi_ = rank < world - 1 ? cut(rank) + 3.0 * rmax : 1e300;
+    build_vox();
     far_bytes_ = Launch<R>::comm_far_bytes();
     far_send_.alloc(far_bytes_);
     far_recv_.alloc(far_bytes_ * (size_t)world);
@@ -867,6 +893,12 @@ template <typename R> int Engine<R>::comm_destroy()
     ev_sent_ = ev_consumed_ = nullptr;
     A_.comm.on = 0;
     comm_on_ = false;
+    if (!closing_ && (vox_xlo_ > -1e299 || vox_xhi_ < 1e299)) {   // back to the index of the whole surface
+        vox_xlo_ = -1e300;
+        vox_xhi_ = 1e300;
+        build_vox();
+        sorted_ = false;
+    }
     return 0;
 }
 
