@@ -662,7 +662,7 @@ void Engine<R>::ingest(int N, const double* uv, const int* heading, const int* v
     in.vid = vid ? (const int*)put(vid, sizeof(int) * (size_t)N) : nullptr;
     in.r3d = r3d ? (const double*)put(r3d, sizeof(double) * 3 * (size_t)N) : nullptr;
     in.ids = ids ? (const uint32_t*)put(ids, sizeof(uint32_t) * (size_t)N) : nullptr;
-    IoLaunch<R>::ingest(N, in, dst, d_trig_d_.p, stream_);
+    IoLaunch<R>::ingest(N, in, dst, stream_);
     launches_++;
 }
 

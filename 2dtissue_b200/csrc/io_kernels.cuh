@@ -27,7 +27,7 @@ struct HostViewOut {
 };
 
 template <typename R>
-__global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleArrays<R> p, const double2* __restrict__ trig)
+__global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleArrays<R> p)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -44,17 +44,6 @@ __global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleAr
     Real2<R> z = {R(0), R(0)};
     p.rdot[i] = z;
     p.color[i] = 0;
-    if (p.cs) {   // (cos, sin) of the heading as the reference's libm gives them (host-built table), CUDA libm outside it
-        const int n = in.heading ? in.heading[i] : 0;
-        double2 t;
-        if (n >= TRIG_MIN && n <= TRIG_MAX) {
-            t = trig[n - TRIG_MIN];
-        } else {
-            const double r = (double)n * DEG_TO_RAD_D;
-            t = make_double2(cos(r), sin(r));
-        }
-        p.cs[i] = t;
-    }
 }
 
 // slot s holds the particle that sits at index aux[s].w of the caller's arrays.  Slab mode (offsets != null): halo
@@ -131,7 +120,7 @@ template <typename R> __global__ void __launch_bounds__(256) k_outN(int N, int c
 }
 
 template <typename R> struct IoLaunch {
-    static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, const double2* trig, cudaStream_t s);
+    static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s);
     static void egest(int resident, int N, const int* offsets, const ParticleArrays<R>& p, const Real2<R>* F,
                       const int* new_heading, const HostViewOut& out, cudaStream_t s);
     static void owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s);
@@ -142,9 +131,9 @@ template <typename R> struct IoLaunch {
 
 #ifdef T2D_IO_IMPL
 template <typename R>
-void IoLaunch<R>::ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, const double2* trig, cudaStream_t s)
+void IoLaunch<R>::ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s)
 {
-    if (N > 0) k_ingest<R><<<(N + 255) / 256, 256, 0, s>>>(N, in, p, trig);
+    if (N > 0) k_ingest<R><<<(N + 255) / 256, 256, 0, s>>>(N, in, p);
 }
 template <typename R>
 void IoLaunch<R>::egest(int resident, int N, const int* offsets, const ParticleArrays<R>& p, const Real2<R>* F,

@@ -243,12 +243,18 @@ template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<
     const uint32_t key = a.key[i];
     if (key == KEY_DROP) return;   // slab mode: halo copy of the previous step, or a particle that left
     const int s = a.start[key] + (int)a.rank[i];
-    a.alt.pos[s] = a.cur.pos[i];
+    const Pos3<R> P = a.cur.pos[i];
+    a.alt.pos[s] = P;
     a.alt.uv[s] = a.cur.uv[i];
     a.alt.aux[s] = a.cur.aux[i];
     a.alt.rdot[s] = a.cur.rdot[i];
     a.alt.color[s] = a.cur.color[i];
-    if (a.cur.cs) a.alt.cs[s] = a.cur.cs[i];
+    if (a.alt.cs) {   // fp32 Euclid path: (cos, sin) of the heading for the neighbour sums of the next step, made here once per
+                      // particle from the host-built table instead of being carried through the step kernel and the sort
+        unsigned long long fb = 0;
+        a.alt.cs[s] = trig_lookup(a.trig_d, (int)P.w, fb);
+        if (fb) atomicAdd(&a.counters->trig_fallbacks, fb);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -566,7 +572,6 @@ template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREAD
             a.alt.aux[i] = make_int4(vid, face, ai.z, ai.w);
             a.alt.rdot[i] = rd;
             a.alt.color[i] = color;
-            if (a.alt.cs) a.alt.cs[i] = trig_lookup(a.trig_d, n_new, bc.trig_fb);
             if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
                 const uint32_t key = bucket_key<R>(a, X, vid, bc);
                 a.key[i] = key;
@@ -795,15 +800,11 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
             const int which = lift_to_3d<R>(p.x, p.y, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv);
             const int vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
             const Pos3<R> X = {Xv[0], Xv[1], Xv[2], (R)n_new};
-            unsigned long long tfb = 0;
-            const double2 ncs = trig_lookup(a.trig_d, n_new, tfb);
-            if (tfb) atomicAdd(&a.counters->trig_fallbacks, tfb);
             a.alt.pos[i] = X;
             a.alt.uv[i] = p;
             a.alt.aux[i] = make_int4(vid, f, ai.z, ai.w);
             a.alt.rdot[i] = rd;
             a.alt.color[i] = color;
-            a.alt.cs[i] = ncs;
             if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
                 int c[3];
                 cell_coords<R>(a.vox, X, c);
@@ -1204,7 +1205,6 @@ template <typename R> __global__ void __launch_bounds__(256) k_comm_unpack(StepA
             a.cur.aux[slot] = make_int4(0, -1, g.id, ORIGIN_GHOST);
             a.cur.color[slot] = 0;
         }
-        if (a.cur.cs) a.cur.cs[slot] = trig_lookup(a.trig_d, (int)P.w, bc.trig_fb);
         const uint32_t key = bucket_key<R>(a, P, vid, bc);
         a.key[slot] = key;
         a.rank[slot] = (uint32_t)atomicAdd(&a.count[key], 1);
@@ -1246,7 +1246,6 @@ template <typename R> __global__ void __launch_bounds__(256) k_comm_unpack_far(S
                         a.cur.aux[slot] = make_int4(0, -1, r.aux.z, ORIGIN_GHOST);
                         a.cur.color[slot] = 0;
                     }
-                    if (a.cur.cs) a.cur.cs[slot] = trig_lookup(a.trig_d, (int)r.pos.w, bc.trig_fb);
                     const uint32_t key = bucket_key<R>(a, r.pos, r.aux.x, bc);
                     a.key[slot] = key;
                     a.rank[slot] = (uint32_t)atomicAdd(&a.count[key], 1);

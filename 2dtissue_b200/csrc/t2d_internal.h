@@ -61,7 +61,7 @@ template <typename R> struct ParticleArrays {
     int4* aux = nullptr;      // x = nearest-vertex id (vertices_3D_active), y = face, z = global id, w = index in the caller's arrays
     Real2<R>* rdot = nullptr; // velocity of the last step (r_dot)
     int* color = nullptr;     // neighbour count of the last step (particles_color)
-    double2* cs = nullptr;    // fp32 Euclid path only: (cos, sin) of the heading as the reference's libm gives them
+    double2* cs = nullptr;    // fp32 Euclid path only: (cos, sin) of the heading as the reference's libm gives them; made by k_scatter
 };
 
 // ---- multi-GPU slabs: message records and the device-side description of one rank's slab ----

@@ -12,7 +12,7 @@ echo "== bench" ; timeout 600 python bench.py --steps 50 --warmup 5 > $OUT/bench
 for W in c2 c3; do timeout 300 python bench.py --workload $W --steps 20 --warmup 3 > $OUT/bench_$W.json 2> $OUT/bench_$W.err; echo "bench $W rc=$?"; cat $OUT/bench_$W.json; done
 echo "== bench reference" ; timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json
 echo "== ncu launches"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 10 --warmup 50 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_step_euclid|k_scatter|k_scan_apply' -s 15 -c 6 -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_step_euclid|k_scatter|k_scan_apply' -s 150 -c 6 -f -o $OUT/prof python bench.py --steps 2 --warmup 50 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT
