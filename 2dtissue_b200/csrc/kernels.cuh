@@ -727,7 +727,10 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
                 const float d2 = dx * dx + dy * dy + dz * dz;
                 // _2DTissue::count_particle_neighbors: 0 != d <= 2.4 sigma, as ONE unsigned compare on the bit patterns
                 // (d2 >= 0: bits(d2) - 1 wraps to 0xffffffff for d2 == 0 and keeps the order of positive floats)
-                color += (__float_as_uint(d2) - 1u < r2c_bits) ? 1 : 0;
+                // (as predicated add: the compiler's select form costs one more instruction per candidate)
+                asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tadd.u32 t, %1, -1;\n\tsetp.lt.u32 p, t, %2;\n\t@p add.s32 %0, %0, 1;\n\t}"
+                    : "+r"(color)
+                    : "r"(__float_as_uint(d2)), "r"(r2c_bits));
                 if (d2 < r2s) {
                     pair_term(cs, uv, jb + t, d2, ui, g1, g0, acc);
                     hits++;
