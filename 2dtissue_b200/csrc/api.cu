@@ -78,7 +78,7 @@ struct EngineBase {
                           const uint32_t* ids, bool project) = 0;
     virtual int download(double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, int* face) = 0;
     virtual int step(int nsteps) = 0;
-    virtual int step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color) = 0;
+    virtual int step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, bool reproject) = 0;
     virtual int observables(double* out) = 0;
     virtual int get_counters(t2d_counters* out) = 0;
     virtual int reset_counters() = 0;
@@ -138,7 +138,7 @@ template <typename R> class Engine : public EngineBase {
                   bool project) override;
     int download(double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, int* face) override;
     int step(int nsteps) override;
-    int step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color) override;
+    int step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, bool reproject) override;
     int observables(double* out) override;
     int get_counters(t2d_counters* out) override;
     int reset_counters() override;
@@ -1060,10 +1060,14 @@ template <typename R> int Engine<R>::step(int nsteps)
     return read_fault();
 }
 
-template <typename R> int Engine<R>::step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color)
+template <typename R>
+int Engine<R>::step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, bool reproject)
 {
     if (comm_on_) throw CudaError{"t2d_step_host is not available in slab mode"};
-    set_state(N, uv, heading, vid, r3d, nullptr, false);
+    if (reproject)
+        set_state(N, uv, heading, nullptr, nullptr, nullptr, true);
+    else
+        set_state(N, uv, heading, vid, r3d, nullptr, false);
     int fault = step(1);
     download(uv, heading, vid, r3d, rdot, color, nullptr);
     return fault;
@@ -1358,7 +1362,12 @@ int t2d_step(t2d_ctx* ctx, int32_t nsteps) { T2D_TRY(ctx, return ctx->eng->step(
 int t2d_step_host(t2d_ctx* ctx, int32_t N, double* uv, int32_t* heading, int32_t* vid, double* r3d, double* rdot,
                   int32_t* color)
 {
-    T2D_TRY(ctx, return ctx->eng->step_host(N, uv, heading, vid, r3d, rdot, color);)
+    T2D_TRY(ctx, return ctx->eng->step_host(N, uv, heading, vid, r3d, rdot, color, false);)
+}
+int t2d_step_host_uv(t2d_ctx* ctx, int32_t N, double* uv, int32_t* heading, int32_t* vid_out, double* r3d_out, double* rdot,
+                     int32_t* color)
+{
+    T2D_TRY(ctx, return ctx->eng->step_host(N, uv, heading, vid_out, r3d_out, rdot, color, true);)
 }
 int t2d_observables(t2d_ctx* ctx, double out[T2D_OBS_LEN]) { T2D_TRY(ctx, return ctx->eng->observables(out);) }
 int t2d_get_counters(t2d_ctx* ctx, t2d_counters* out) { T2D_TRY(ctx, return ctx->eng->get_counters(out);) }

@@ -163,10 +163,11 @@ class Context:
     def step(self, nsteps=1):
         return self._chk(self.L.t2d_step(self.h, nsteps), "t2d_step")
 
-    def step_host(self, uv, heading, vid, r3d, rdot, color):
-        """In/out numpy arrays in the reference's layouts (the literal perform_particle_simulation drop-in)."""
-        return self._chk(self.L.t2d_step_host(self.h, heading.size, _d(uv), _i(heading), _i(vid), _d(r3d), _d(rdot),
-                                              _i(color)), "t2d_step_host")
+    def step_host(self, uv, heading, vid, r3d, rdot, color, reproject=False):
+        """In/out numpy arrays in the reference's layouts (the literal perform_particle_simulation drop-in).
+        reproject=True: only uv and heading are uploaded, the device re-projects uv (vid, r3d are outputs only)."""
+        fn = self.L.t2d_step_host_uv if reproject else self.L.t2d_step_host
+        return self._chk(fn(self.h, heading.size, _d(uv), _i(heading), _i(vid), _d(r3d), _d(rdot), _i(color)), "t2d_step_host")
 
     def observables(self):
         out = np.zeros(_lib.OBS_LEN)

@@ -304,14 +304,16 @@ def main_ours(args, rank, world, local_rank):
         s = ctx.download(("uv", "n", "vid", "r3d"))
         h_uv, h_n, h_vid, h_r3d = pin(s["uv"]), pin(s["n"]), pin(s["vid"]), pin(s["r3d"])
         h_rdot, h_col = pin(np.zeros(2 * Nloc)), pin(np.zeros(Nloc, dtype=np.int32))
-        ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col)
+        # t2d_step_host_uv: r_UV and n go up (r_3D / vertices_3D_active are functions of r_UV and are re-projected on the
+        # device), everything the reference's step produces comes back
+        ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col, reproject=True)
         barrier()
         te = time.perf_counter()
         for _ in range(e2e_steps):
-            ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col)
+            ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col, reproject=True)
         barrier()
         e2e_s = time.perf_counter() - te
-        h2d = Nloc * (16 + 4 + 4 + 24)
+        h2d = Nloc * (16 + 4)
         d2h = Nloc * (16 + 4 + 4 + 24 + 16 + 4)
     else:
         pinz = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()

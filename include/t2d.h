@@ -137,6 +137,11 @@ int t2d_step(t2d_ctx* ctx, int32_t nsteps);
  * upload -> one step -> download.  This is the literal drop-in for perform_particle_simulation. */
 int t2d_step_host(t2d_ctx* ctx, int32_t N, double* uv, int32_t* heading, int32_t* vid, double* r3d, double* rdot,
                   int32_t* color);
+/* the same, but only r_UV and n travel to the device: r_3D and vertices_3D_active are functions of r_UV
+ * (CellHelper::get_r3d, what the previous step left in the driver's members), so the device re-projects the uploaded
+ * r_UV instead of receiving them — 20 instead of 48 bytes per particle over PCIe.  vid and r3d are outputs only. */
+int t2d_step_host_uv(t2d_ctx* ctx, int32_t N, double* uv, int32_t* heading, int32_t* vid_out, double* r3d_out, double* rdot,
+                     int32_t* color);
 int t2d_observables(t2d_ctx* ctx, double out[T2D_OBS_LEN]);
 int t2d_get_counters(t2d_ctx* ctx, t2d_counters* out);
 int t2d_reset_counters(t2d_ctx* ctx);

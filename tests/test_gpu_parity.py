@@ -273,6 +273,24 @@ def test_step_host_is_the_dropin(t2d, chart, hop_table):
     assert np.array_equal(vid[good], z["vid1"][good])
 
 
+def test_step_host_uv_reprojects_on_the_device(t2d, chart):
+    """t2d_step_host_uv uploads only r_UV and n; r_3D / vertices_3D_active are re-projected on the device, which is
+    what the previous step left on the host: same result as the full-state drop-in, bit for bit."""
+    z = golden("step_euclid_N2000.npz")
+    v0, k, sigma, h = (float(x) for x in z["params"])
+    N = z["n0"].size
+    ctx = t2d.Context(chart, v0=v0, k=k, sigma=sigma, step_size=h, neigh_mode=1, capacity=N)
+    a = [z["uv0"].copy(), z["n0"].copy(), z["vid0"].copy(), z["r3d0"].copy(), np.zeros(2 * N), np.zeros(N, dtype=np.int32)]
+    b = [z["uv0"].copy(), z["n0"].copy(), np.zeros(N, dtype=np.int32), np.zeros(3 * N), np.zeros(2 * N), np.zeros(N, dtype=np.int32)]
+    for _ in range(2):
+        fa = ctx.step_host(*a)
+        fb = ctx.step_host(*b, reproject=True)
+        assert fa == fb
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert np.array_equal(a[5], z["color2"]) if "color2" in z.files else True
+
+
 def test_upload_order_independence(t2d, chart, hop_table):
     """Results are a function of (id -> state), not of device order or upload order."""
     N = 4000
