@@ -619,8 +619,9 @@ struct PairAcc {
 };
 
 // one in-range pair.  F_ij / d = -k (2 sigma - d) / (2 sigma d) = (-k) / d + k / (2 sigma): one FMA on 1/d
-// (ForceHelper.cpp:84-104).  d = 0 is the particle itself or one coincident with it (ForceHelper.cpp:59-62 sets
-// d := 0.001): ui - uj = 0 there, so the term vanishes for any finite 1/d — the clamp only keeps it finite.
+// (ForceHelper.cpp:84-104).  d = 0 -> d := 0.001 (ForceHelper.cpp:59-62): the particle itself (ui - uj = 0, no force)
+// or one whose 3-D position coincides with it in fp32 while its uv does not — common inside the dense clumps the
+// lift produces, so the rule matters: without it 1/d is unbounded and a single pair throws both particles off the chart.
 __device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const Real2<float>* __restrict__ uv, int j, float d2,
                                           const Real2<float>& ui, float g1, float g0, PairAcc& acc)
 {
@@ -628,7 +629,7 @@ __device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const 
     const Real2<float> uj = uv[j];
     acc.mx += t.x;
     acc.my += t.y;
-    const float g = fmaf(rsqrtf(fmaxf(d2, 1e-36f)), g1, g0);
+    const float g = fmaf(d2 == 0.0f ? 1000.0f : rsqrtf(d2), g1, g0);
     acc.fx = fmaf(g, ui.x - uj.x, acc.fx);
     acc.fy = fmaf(g, ui.y - uj.y, acc.fy);
 }
