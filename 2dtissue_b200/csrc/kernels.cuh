@@ -416,7 +416,7 @@ __device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> 
 //                        UV point location deferred to a CTA-wide compacted pass for the particles that left
 //                        their previous face.
 // ---------------------------------------------------------------------------------------------------
-constexpr int EUCLID_KMAX = 48;
+constexpr int EUCLID_KMAX = 192;   // in-range neighbours ordered in the per-thread list (local memory); longer rows: repeated selection
 #ifndef T2D_STEP_THREADS
 #define T2D_STEP_THREADS 128
 #endif
