@@ -497,14 +497,21 @@ template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREAD
         overflow = cnt > EUCLID_KMAX;
         if ((unsigned long long)cnt > bc.max_row) bc.max_row = cnt;
         if (!overflow) {
-            for (int p = 1; p < cnt; ++p) {   // insertion sort by (id, slot)
-                unsigned long long kx = list[p];
-                int q = p - 1;
-                while (q >= 0 && list[q] > kx) {
-                    list[q + 1] = list[q];
-                    --q;
+            // Shell sort by (id, slot), Ciura gaps: ~k^1.3 moves instead of k^2/4 — rows of 50-200 neighbours are
+            // common inside the clumps the lift produces (ncu: the plain insertion sort was 31 % of the kernel)
+            const int gaps[6] = {132, 57, 23, 10, 4, 1};
+#pragma unroll 1
+            for (int gi = 0; gi < 6; ++gi) {
+                const int gap = gaps[gi];
+                for (int p = gap; p < cnt; ++p) {
+                    unsigned long long kx = list[p];
+                    int q = p - gap;
+                    while (q >= 0 && list[q] > kx) {
+                        list[q + gap] = list[q];
+                        q -= gap;
+                    }
+                    list[q + gap] = kx;
                 }
-                list[q + 1] = kx;
             }
         } else {
             bc.order_fb++;   // long row: ordered by repeated selection instead of the register list (still exact)
