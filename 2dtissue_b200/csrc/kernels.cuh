@@ -1,13 +1,15 @@
 // kernels.cuh — the step's CUDA kernels, templated on the arithmetic type.
 //
-//   k_bin             bucket key of every resident particle + arrival rank + histogram (K1; after uploads only —
-//                     during stepping the producing kernel emits the next keys itself)
-//   k_scatter         counting-sort scatter of the SoA state into bucket order (K2)
-//   k_step_euclid     stages 2-5 FUSED for the Euclidean criterion: sparse-voxel cell list, 2x2x2 octant
-//                     stencil, force + alignment (+ noise), Euler, seam re-entry, re-projection, next key (K3-K5)
-//   k_neigh_table     stages 2-4a for the vertex-distance-table criterion: one CTA per bucket, neighbour
-//                     buckets from the thresholded CSR row, shared-memory staging, exact ascending-id sums (K3)
-//   k_wrap_project    table mode: seam re-entry + UV point location + 3-D lift + validation + next key (K4+K5)
+//   k_bin               bucket key of every resident particle + arrival rank + histogram (K1; after uploads only —
+//                       during stepping the producing kernel emits the next keys itself)
+//   k_scatter           counting-sort scatter of the SoA state into bucket order (K2); makes the fp32 path's cos/sin array
+//   k_step_euclid_fast  stages 2-5 FUSED for the Euclidean criterion, fp32: sparse row index of the cell list, 3 x 3 rows
+//                       of 3-cell x-runs, force + alignment (+ noise), Euler, seam re-entry, re-projection, next key
+//   k_step_euclid_exact the same, fp64 parity path: in-range neighbours summed in ascending global id
+//   k_neigh_table       stages 2-4a for the vertex-distance-table criterion: one CTA per bucket, neighbour
+//                       buckets from the thresholded CSR row, shared-memory staging, exact ascending-id sums (K3)
+//   k_wrap_project      table mode: seam re-entry + UV point location + 3-D lift + validation + next key (K4+K5)
+//   k_comm_pack / k_comm_unpack / k_comm_unpack_far   slab exchange (multi-GPU): classify + pack, append what arrived
 //
 // No tensor cores anywhere: the work is gather/scatter + O(10^2) flop per particle.
 #pragma once
