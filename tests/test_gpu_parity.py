@@ -392,3 +392,52 @@ def test_table_mode_1M_hop_table_runs(t2d, chart, hop_table):
     assert np.all((s["vid"] >= 0) & (s["vid"] < ctx.V))
     # in table mode all particles of one vertex bucket share one neighbour set -> pairs >> N
     assert c["pairs_in_range"] > N
+
+
+# ------------------------------------------------------------------------------------------------------
+# edge cases: empty and tiny inputs, particles exactly on the chart border, capacity limit
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_empty_and_single_particle(t2d, chart, hop_table, precision, mode):
+    tab = hop_table if mode == 0 else None
+    ctx = t2d.Context(chart, table=tab, neigh_mode=mode, precision=precision, capacity=16, sigma=0.4166666666666667)
+    ctx.set_particles(np.zeros(0), np.zeros(0, dtype=np.int32))            # N = 0: every call is a no-op
+    assert ctx.step(3) == 0
+    out = ctx.download()
+    assert all(v.size == 0 for v in out.values())
+    ctx.set_particles(np.array([0.37, 0.61]), np.array([123], dtype=np.int32))   # one isolated particle
+    assert ctx.step(1) == 0
+    out = ctx.download()
+    assert out["color"][0] == 0                                            # no neighbour
+    assert out["n"][0] in (122, 123)                                       # mean of its own heading (truncation tie)
+    speed = float(np.hypot(out["rdot"][0], out["rdot"][1]))
+    assert abs(speed - 0.1) < 1e-6                                         # |F| = 0: speed = v0
+
+
+def test_capacity_is_enforced(t2d, chart):
+    ctx = t2d.Context(chart, neigh_mode=1, capacity=8, sigma=0.05)
+    uv, n = t2d.seed_particles(9, seed=3)
+    with pytest.raises(t2d.T2DError):
+        ctx.set_particles(uv, n)
+
+
+def test_particles_on_the_chart_border_stay_inside(t2d, chart, oracle):
+    """Closed unit square: points exactly on the border are inside (MCL test_SurfaceParametrization.cpp:59-123); they must be
+    located, lifted and stepped like the oracle does."""
+    uv = np.array([0.0, 1.0, 0.5, 0.0, 1.0, 0.25,     # x
+                   0.0, 1.0, 0.0, 0.5, 0.25, 1.0])    # y
+    n = np.array([0, 90, 180, 270, 45, 315], dtype=np.int32)
+    ctx = t2d.Context(chart, neigh_mode=1, capacity=8, sigma=0.05)
+    ctx.set_particles(uv, n)
+    s0 = ctx.download()
+    r3d_o, vid_o, face_o = oracle.get_r3d(uv)
+    assert np.array_equal(s0["vid"], vid_o) and np.array_equal(s0["r3d"], r3d_o)
+    fault = ctx.step(1)
+    g = ctx.download()
+    o = oracle.step(uv, n, vid_o, r3d_o, 0.1, 1.0, 0.05, 0.001, mode=1)
+    assert fault == o["fault"]
+    assert np.all((g["uv"] >= 0) & (g["uv"] <= 1))
+    good = g["n"] == o["n"]
+    assert np.array_equal(g["uv"][np.concatenate([good, good])], o["uv"][np.concatenate([good, good])])
+    assert np.array_equal(g["vid"][good], o["vid"][good])
