@@ -222,7 +222,7 @@ def main_reference(args, rank, world):
             "config": {"workload": spec["name"]},
             "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -321,7 +321,7 @@ def main_ours(args, rank, world, local_rank):
 
     if args.no_cpu_baseline:
         if rank == 0:
-            print(json.dumps({"profiler_run": True, "ms_per_step": ms_per_step, "kernel_ms": prof}))
+            emit(json.dumps({"profiler_run": True, "ms_per_step": ms_per_step, "kernel_ms": prof}))
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -400,9 +400,30 @@ def main_ours(args, rank, world, local_rank):
                                  "port": run_port_sample(spec) if kind == "reference" else None},
                 "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d * world),
                         "d2h_bytes_per_step": int(d2h * world), "steps": e2e_steps}}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: everything libraries print there while the bench runs (NCCL's version
+    banner, for one) is sent to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -419,6 +440,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    quiet_stdout()
     if args.impl == "reference":
         main_reference(args, rank, world)
     else:
