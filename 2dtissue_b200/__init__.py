@@ -14,4 +14,4 @@ from .chart import load_chart, refine_chart, save_chart  # noqa: F401
 from .host import (FAULT_LOST, FAULT_NONFINITE, FAULT_WRAP_CAP, NEIGH_EUCLID, NEIGH_TABLE, PRECISION_FP32, PRECISION_FP64, TABLE_DENSE_F32, TABLE_DENSE_F64,  # noqa: F401
                    TABLE_DENSE_U8, TABLE_HOPS_FROM_MESH, TABLE_NONE, Context, LostParticlesError, Particle, System,
                    T2DError, Tissue2D, seed_particles, FAULT_MIGRATION, FAULT_COMM_OVERFLOW, LocalSlabGroup,
-                   comm_unique_id, merge_by_id, partition_by_slab, slab_cuts, slab_of)
+                   comm_unique_id, merge_by_id, partition_by_slab, slab_cuts, slab_of, LIFT_REFERENCE, LIFT_BARYCENTRIC)

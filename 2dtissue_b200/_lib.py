@@ -22,7 +22,7 @@ class Table(C.Structure):
 class Params(C.Structure):
     _fields_ = [("v0", C.c_double), ("k", C.c_double), ("sigma", C.c_double), ("step_size", C.c_double),
                 ("eta", C.c_double), ("color_factor", C.c_double), ("seed", C.c_uint64), ("neigh_mode", C.c_int32),
-                ("precision", C.c_int32), ("capacity", C.c_int32), ("reserved", C.c_int32)]
+                ("precision", C.c_int32), ("capacity", C.c_int32), ("lift_mode", C.c_int32)]
 
 
 class Counters(C.Structure):

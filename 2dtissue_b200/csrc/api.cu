@@ -341,6 +341,7 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     A_.cr = d_cr_.p;
     A_.work_counter = d_work_.p;
     A_.mode = P_.neigh_mode;
+    A_.mesh.lift_mode = P_.lift_mode;
     A_.write_F = 0;
     apply_params();
     CK(cudaStreamSynchronize(stream_));
@@ -662,7 +663,8 @@ template <typename R> void Engine<R>::apply_params()
 
 template <typename R> int Engine<R>::set_params(const t2d_params* p)
 {
-    if (p->neigh_mode != P_.neigh_mode || p->precision != P_.precision) throw CudaError{"neigh_mode/precision are fixed at create"};
+    if (p->neigh_mode != P_.neigh_mode || p->precision != P_.precision || p->lift_mode != P_.lift_mode)
+        throw CudaError{"neigh_mode/precision/lift_mode are fixed at create"};
     int cap = P_.capacity;
     P_ = *p;
     P_.capacity = cap;

@@ -98,19 +98,30 @@ template <typename R> T2D_HD R point_triangle_distance(R px, R py, R ax, R ay, R
 // UV -> 3-D lift after the arg-min, CellHelper::calculate_barycentric_3D_coord, CellHelper.cpp:119-159.
 // ua/ub/uc: UV corners; A/B/C: 3-D corners; returns which corner (0,1,2) is nearest to the lifted point.
 // ---------------------------------------------------------------------------------------------------
+// barycentric = false: the reference's weights (normalised UV distances to the corners); true: T2D_LIFT_BARYCENTRIC,
+// w_a = [(b-p) x (c-p)] / [(b-a) x (c-a)], w_b = [(c-p) x (a-p)] / same, w_c = 1 - w_a - w_b (same order in the oracle)
 template <typename R>
-T2D_HD int lift_to_3d(R px, R py, R uax, R uay, R ubx, R uby, R ucx, R ucy, const R* A, const R* B, const R* C, R* X)
+T2D_HD int lift_to_3d(R px, R py, R uax, R uay, R ubx, R uby, R ucx, R ucy, const R* A, const R* B, const R* C, R* X,
+                      bool barycentric = false)
 {
     R dax = px - uax, day = py - uay;
     R dbx = px - ubx, dby = py - uby;
     R dcx = px - ucx, dcy = py - ucy;
-    R w_a = rsqrt_exact<R>(dax * dax + day * day);
-    R w_b = rsqrt_exact<R>(dbx * dbx + dby * dby);
-    R w_c = rsqrt_exact<R>(dcx * dcx + dcy * dcy);
-    R sum_weights = w_a + w_b + w_c;
-    w_a = w_a / sum_weights;
-    w_b = w_b / sum_weights;
-    w_c = w_c / sum_weights;
+    R w_a, w_b, w_c;
+    if (barycentric) {
+        R den = (ubx - uax) * (ucy - uay) - (uby - uay) * (ucx - uax);
+        w_a = (dbx * dcy - dby * dcx) / den;
+        w_b = (dcx * day - dcy * dax) / den;
+        w_c = (R(1) - w_a) - w_b;
+    } else {
+        w_a = rsqrt_exact<R>(dax * dax + day * day);
+        w_b = rsqrt_exact<R>(dbx * dbx + dby * dby);
+        w_c = rsqrt_exact<R>(dcx * dcx + dcy * dcy);
+        R sum_weights = w_a + w_b + w_c;
+        w_a = w_a / sum_weights;
+        w_b = w_b / sum_weights;
+        w_c = w_c / sum_weights;
+    }
     R da2 = 0, db2 = 0, dc2 = 0;
     R e[3][3];
     for (int k = 0; k < 3; ++k) {

@@ -368,7 +368,7 @@ __device__ __forceinline__ void project_point(const DevMesh<R>& m, R px, R py, i
     int4 tv = m.tri_vid[f];
     Pos3<R> A = m.x3d[tv.x], B = m.x3d[tv.y], C = m.x3d[tv.z];
     R Av[3] = {A.x, A.y, A.z}, Bv[3] = {B.x, B.y, B.z}, Cv[3] = {C.x, C.y, C.z}, Xv[3];
-    int which = lift_to_3d<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv);
+    int which = lift_to_3d<R>(px, py, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv, m.lift_mode == T2D_LIFT_BARYCENTRIC);
     face = f;
     vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
     X.x = Xv[0];
@@ -810,7 +810,8 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
             const Pos3<R> A = a.mesh.x3d[tv.x], B = a.mesh.x3d[tv.y], C = a.mesh.x3d[tv.z];
             const R Av[3] = {A.x, A.y, A.z}, Bv[3] = {B.x, B.y, B.z}, Cv[3] = {C.x, C.y, C.z};
             R Xv[3];
-            const int which = lift_to_3d<R>(p.x, p.y, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv);
+            const int which = lift_to_3d<R>(p.x, p.y, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv,
+                                            a.mesh.lift_mode == T2D_LIFT_BARYCENTRIC);
             const int vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
             const Pos3<R> X = {Xv[0], Xv[1], Xv[2], (R)n_new};
             a.alt.pos[i] = X;

@@ -21,6 +21,7 @@ template <typename R> struct alignas(16) Pos3 {    // 3-D point; w carries the p
 
 template <typename R> struct DevMesh {
     int V = 0, F = 0, G = 0;                 // G x G uniform grid over the UV square
+    int lift_mode = 0;                       // T2D_LIFT_*
     const TriUV<R>* tri = nullptr;           // [F]
     const int4* tri_vid = nullptr;           // [F] vertex ids (a,b,c,-)
     const Pos3<R>* x3d = nullptr;            // [V]

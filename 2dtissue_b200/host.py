@@ -13,6 +13,7 @@ TABLE_NONE, TABLE_DENSE_F64, TABLE_DENSE_F32, TABLE_DENSE_U8, TABLE_HOPS_FROM_ME
 NEIGH_TABLE, NEIGH_EUCLID = 0, 1
 PRECISION_FP64, PRECISION_FP32 = 0, 1
 FAULT_LOST, FAULT_NONFINITE, FAULT_WRAP_CAP, FAULT_MIGRATION, FAULT_COMM_OVERFLOW = 1, 2, 4, 8, 16
+LIFT_REFERENCE, LIFT_BARYCENTRIC = 0, 1   # T2D_LIFT_*
 
 _dp, _ip, _up = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
 
@@ -38,7 +39,7 @@ class Context:
 
     def __init__(self, chart, table=None, table_kind=None, v0=0.1, k=1.0, sigma=0.4166666666666667, step_size=0.001,
                  eta=0.0, color_factor=2.4, seed=0, neigh_mode=NEIGH_TABLE, precision=PRECISION_FP64, capacity=1024,
-                 device=0):
+                 device=0, lift_mode=LIFT_REFERENCE):
         self.L = _lib.load()
         self._uv = np.ascontiguousarray(chart["uv"], dtype=np.float64)
         self._x3d = np.ascontiguousarray(chart["x3d"], dtype=np.float64)
@@ -55,7 +56,7 @@ class Context:
                     np.dtype(np.uint8): TABLE_DENSE_U8}[t.dtype]
             self._table = t
             tab = Table(t.shape[0], kind, t.ctypes.data_as(C.c_void_p))
-        self.params = Params(v0, k, sigma, step_size, eta, color_factor, seed, neigh_mode, precision, capacity, 0)
+        self.params = Params(v0, k, sigma, step_size, eta, color_factor, seed, neigh_mode, precision, capacity, lift_mode)
         h = C.c_void_p()
         rc = self.L.t2d_create(C.byref(mesh), C.byref(tab), C.byref(self.params), device, C.byref(h))
         if rc != 0:

@@ -25,7 +25,7 @@ static void usage(const char* argv0)
               << "  --step-time X                  wired into v0 like the reference (default 0.01)\n"
               << "  --kafka                        not available in this build\n"
               << " extensions:\n"
-              << "  --neigh {table,euclid}  --precision {fp64,fp32}  --sigma X  --noise-eta X  --seed N  --device N\n"
+              << "  --neigh {table,euclid}  --precision {fp64,fp32}  --lift {reference,barycentric}  --sigma X  --noise-eta X  --seed N  --device N\n"
               << "  --data-dir DIR  --load-state FILE  --save-state FILE  --dump-chart FILE  --no-particles  --quiet\n";
 }
 
@@ -53,6 +53,7 @@ int main(int argc, char* argv[])
             else if (a == "--kafka") use_kafka = true;
             else if (a == "--neigh") { std::string v = val(); ext.neigh_mode = v == "euclid" ? T2D_NEIGH_EUCLID : T2D_NEIGH_TABLE; if (v != "euclid" && v != "table") throw std::runtime_error("--neigh must be table or euclid"); }
             else if (a == "--precision") { std::string v = val(); ext.precision = v == "fp32" ? T2D_PRECISION_FP32 : T2D_PRECISION_FP64; if (v != "fp32" && v != "fp64") throw std::runtime_error("--precision must be fp64 or fp32"); }
+            else if (a == "--lift") { std::string v = val(); ext.lift_mode = v == "barycentric" ? T2D_LIFT_BARYCENTRIC : T2D_LIFT_REFERENCE; if (v != "barycentric" && v != "reference") throw std::runtime_error("--lift must be reference or barycentric"); }
             else if (a == "--sigma") sigma = std::stod(val());
             else if (a == "--noise-eta") ext.eta = std::stod(val());
             else if (a == "--seed") ext.seed = std::stoull(val());

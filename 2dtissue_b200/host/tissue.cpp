@@ -36,6 +36,7 @@ Tissue2D::Tissue2D(bool save_data_, bool particle_innenleben, bool free_boundary
     prm.color_factor = 2.4;   // 2DTissue.cpp:262
     prm.seed = ext_.seed;
     prm.neigh_mode = ext_.neigh_mode;
+    prm.lift_mode = ext_.lift_mode;
     prm.precision = ext_.precision;
     prm.capacity = particle_count > 0 ? particle_count : 1;
     if (t2d_create(&mesh, &table, &prm, ext_.device, &gpu) != 0) throw std::runtime_error(t2d_last_error(nullptr));

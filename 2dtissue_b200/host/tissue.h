@@ -36,6 +36,7 @@ struct System {     // Struct.h:25-29
 struct Extensions {
     int neigh_mode = T2D_NEIGH_TABLE;      // --neigh {table,euclid}
     int precision = T2D_PRECISION_FP64;    // --precision {fp64,fp32}
+    int lift_mode = T2D_LIFT_REFERENCE;    // --lift {reference,barycentric}
     double eta = 0.0;                      // --noise-eta
     uint64_t seed = 0;                     // --seed (0: std::random_device like CellHelper.cpp:48-49)
     int device = 0;                        // --device

@@ -58,6 +58,11 @@ typedef struct {
 
 enum { T2D_NEIGH_TABLE = 0, T2D_NEIGH_EUCLID = 1 };
 enum { T2D_PRECISION_FP64 = 0, T2D_PRECISION_FP32 = 1 };
+/* UV -> 3-D lift.  REFERENCE: weights = normalised UV distances to the face's corners (CellHelper.cpp:133-146 — not
+ * barycentric: it pulls every point towards the middle of its face).  BARYCENTRIC: the true barycentric coordinates,
+ * i.e. the piecewise-linear chart the code comments describe; validated against the oracle, which
+ * implements the same option, and statistically — there is no reference output to compare with. */
+enum { T2D_LIFT_REFERENCE = 0, T2D_LIFT_BARYCENTRIC = 1 };
 enum {
     T2D_FAULT_LOST = 1, T2D_FAULT_NONFINITE = 2, T2D_FAULT_WRAP_CAP = 4,
     T2D_FAULT_MIGRATION = 8,      /* reserved (particles that land beyond an adjacent halo strip travel through the far channel) */
@@ -76,7 +81,7 @@ typedef struct {
     int32_t neigh_mode;   /* T2D_NEIGH_* */
     int32_t precision;    /* T2D_PRECISION_* */
     int32_t capacity;     /* max particles resident on this context (owned + halo) */
-    int32_t reserved;
+    int32_t lift_mode;    /* T2D_LIFT_*: 0 = the reference's distance-weighted lift (zero-initialised callers get it) */
 } t2d_params;
 
 /* indices into the array filled by t2d_observables */

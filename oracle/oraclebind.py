@@ -61,6 +61,7 @@ def lib():
         L.t2do_table_u8.argtypes = [C.c_void_p]
         L.t2do_inject_noise.argtypes = [C.c_void_p, _dp]
         L.t2do_set_angle_out.argtypes = [C.c_void_p, _dp]
+        L.t2do_set_lift_mode.argtypes = [C.c_void_p, C.c_int]
         L.t2do_get_r3d.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _ip, _ip, C.c_int, C.POINTER(Stats)]
         L.t2do_tiling.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _ip, C.POINTER(Stats)]
         L.t2do_step.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, _dp, _ip, _ip, _dp, _up, C.c_uint64, _dp, _ip,
@@ -92,6 +93,10 @@ class Oracle:
         self.V, self.F = len(self.uv), len(self.faces)
         self.ctx = self.L.t2do_create(self.V, self.F, _d(self.uv), _d(self.x3d), _i(self.faces))
         self.last_stats = None
+
+    def set_lift_mode(self, mode):
+        """0: the reference's distance-weighted lift; 1: barycentric (the extension of include/t2d.h T2D_LIFT_BARYCENTRIC)."""
+        self.L.t2do_set_lift_mode(self.ctx, int(mode))
 
     def __del__(self):
         try:

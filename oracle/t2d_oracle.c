@@ -32,6 +32,7 @@ struct t2do_ctx {
     /* UV grid for point location */
     int G;
     int *gstart, *gfaces;
+    int lift_mode;            /* 0: the reference's lift (CellHelper.cpp:133-146); 1: true barycentric weights (t2d.h T2D_LIFT_BARYCENTRIC) */
     double* angle_out;        /* optional: receives every particle's mean angle in degrees (before truncation) */
     const double* eta_inject; /* optional per-particle noise (degrees) replacing the Philox draw; borrowed */
     /* table-mode CSR cache */
@@ -239,13 +240,21 @@ static void lift_to_3d(const t2do_ctx* c, int f, double px, double py, double* X
     double dax = px - ua[0], day = py - ua[1];
     double dbx = px - ub[0], dby = py - ub[1];
     double dcx = px - uc[0], dcy = py - uc[1];
-    double w_a = sqrt(dax * dax + day * day);
-    double w_b = sqrt(dbx * dbx + dby * dby);
-    double w_c = sqrt(dcx * dcx + dcy * dcy);
-    double sum_weights = w_a + w_b + w_c;
-    w_a /= sum_weights;
-    w_b /= sum_weights;
-    w_c /= sum_weights;
+    double w_a, w_b, w_c;
+    if (c->lift_mode == 1) { /* extension: barycentric coordinates of p in the UV triangle */
+        double den = (ub[0] - ua[0]) * (uc[1] - ua[1]) - (ub[1] - ua[1]) * (uc[0] - ua[0]);
+        w_a = (dbx * dcy - dby * dcx) / den;
+        w_b = (dcx * day - dcy * dax) / den;
+        w_c = (1.0 - w_a) - w_b;
+    } else {
+        w_a = sqrt(dax * dax + day * day);
+        w_b = sqrt(dbx * dbx + dby * dby);
+        w_c = sqrt(dcx * dcx + dcy * dcy);
+        double sum_weights = w_a + w_b + w_c;
+        w_a /= sum_weights;
+        w_b /= sum_weights;
+        w_c /= sum_weights;
+    }
     for (int k = 0; k < 3; ++k)
         X[k] = (w_a * a[k] + w_b * b[k]) + w_c * cc[k];
     double ea[3], eb[3], ec[3];
@@ -569,6 +578,8 @@ int t2do_set_table_u8(t2do_ctx* c, int V, const uint8_t* D)
 const uint8_t* t2do_table_u8(t2do_ctx* c) { return c->Du8; }
 
 void t2do_inject_noise(t2do_ctx* c, const double* eta_deg) { c->eta_inject = eta_deg; }
+void t2do_set_lift_mode(t2do_ctx* c, int mode) { c->lift_mode = mode; }
+
 void t2do_set_angle_out(t2do_ctx* c, double* buf) { c->angle_out = buf; }
 
 static inline double table_at(const t2do_ctx* c, int a, int b)

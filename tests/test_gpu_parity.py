@@ -441,3 +441,44 @@ def test_particles_on_the_chart_border_stay_inside(t2d, chart, oracle):
     good = g["n"] == o["n"]
     assert np.array_equal(g["uv"][np.concatenate([good, good])], o["uv"][np.concatenate([good, good])])
     assert np.array_equal(g["vid"][good], o["vid"][good])
+
+
+# ------------------------------------------------------------------------------------------------------
+# extension: true barycentric lift, oracle-checked
+# ------------------------------------------------------------------------------------------------------
+def test_barycentric_lift_vs_oracle(t2d, chart, oracle):
+    N = 20000
+    uv, n = t2d.seed_particles(N, seed=501)
+    sigma = float(np.sqrt(0.5 * 451.3 / (np.pi * N)))
+    oracle.set_lift_mode(1)
+    try:
+        ctx = t2d.Context(chart, v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=t2d.NEIGH_EUCLID, capacity=N,
+                          lift_mode=t2d.LIFT_BARYCENTRIC)
+        ctx.set_particles(uv, n)
+        s0 = ctx.download()
+        r3d_o, vid_o, face_o = oracle.get_r3d(uv)
+        assert np.array_equal(s0["face"], face_o) and np.array_equal(s0["vid"], vid_o)
+        assert np.array_equal(s0["r3d"], r3d_o), "fp64 barycentric lift expected bit-identical (same op order, no FMA)"
+        uv_c, n_c, vid_c, r3d_c = uv, n, vid_o, r3d_o
+        for step in range(3):
+            o = oracle.step(uv_c, n_c, vid_c, r3d_c, 0.1, 1.0, sigma, 0.001, mode=1)
+            ctx.set_state(uv_c, n_c, vid_c, r3d_c)
+            assert ctx.step(1) == o["fault"]
+            g = ctx.download()
+            nbad, nontie = heading_mismatch_report(g["n"], o["n"], o["angle"])
+            assert nontie == 0
+            assert np.array_equal(g["color"], o["color"]) and np.array_equal(g["rdot"], o["rdot"])
+            good = g["n"] == o["n"]
+            g3 = np.concatenate([good, good, good])
+            assert np.array_equal(g["vid"][good], o["vid"][good]) and np.array_equal(g["face"][good], o["face"][good])
+            assert np.array_equal(g["r3d"][g3], o["r3d"][g3])
+            uv_c, n_c, vid_c, r3d_c = o["uv"], o["n"], o["vid"], o["r3d"]
+        # fp32 fast path with the same lift: within the fast-path tolerance of the fp64 result
+        c32 = t2d.Context(chart, v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=t2d.NEIGH_EUCLID, capacity=N,
+                          precision=t2d.PRECISION_FP32, lift_mode=t2d.LIFT_BARYCENTRIC)
+        c32.set_particles(uv, n)
+        a = c32.download()
+        assert np.max(np.abs(a["r3d"] - r3d_o)) < 1e-4 and (a["vid"] == vid_o).mean() > 0.999
+        assert c32.step(3) == 0
+    finally:
+        oracle.set_lift_mode(0)

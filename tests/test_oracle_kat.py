@@ -151,3 +151,42 @@ def test_inside_predicate_pins(oracle_mod):
     N = ins.size
     got = np.array([L.t2do_inside(float(uv[i]), float(uv[N + i])) for i in range(N)])
     assert np.array_equal(got, ins)
+
+
+def test_barycentric_lift_extension(chart):
+    """T2D_LIFT_BARYCENTRIC in the oracle: the lifted point lies in the plane of its 3-D triangle, the
+    weights reproduce the corners, and the default mode is untouched (the golden tests above run with it)."""
+    from oracle import oraclebind
+    orc = oraclebind.Oracle(chart)
+    rng = np.random.default_rng(3)
+    N = 5000
+    uv = rng.random(2 * N)
+    r_ref, vid_ref, face_ref = orc.get_r3d(uv)
+    orc.set_lift_mode(1)
+    r_b, vid_b, face_b = orc.get_r3d(uv)
+    orc.set_lift_mode(0)
+    assert np.array_equal(face_b, face_ref)                       # point location does not depend on the lift
+    faces, x3d, uvv = chart["faces"], chart["x3d"], chart["uv"]
+    A, B, Cc = (x3d[faces[face_b][:, k]] for k in range(3))
+    P = np.stack([r_b[:N], r_b[N:2 * N], r_b[2 * N:]], 1)
+    nrm = np.cross(B - A, Cc - A)
+    dist = np.abs(np.einsum("ij,ij->i", P - A, nrm)) / np.linalg.norm(nrm, axis=1)
+    assert dist.max() < 1e-9                                      # in the triangle's plane
+    # independent barycentric evaluation in UV
+    a, b, c = (uvv[faces[face_b][:, k]] for k in range(3))
+    p = np.stack([uv[:N], uv[N:]], 1)
+    T = np.stack([b - a, c - a], 2)
+    lam = np.linalg.solve(T, (p - a)[:, :, None])[:, :, 0]
+    Q = A + lam[:, :1] * (B - A) + lam[:, 1:] * (Cc - A)
+    assert np.max(np.abs(Q - P)) < 1e-9
+    # the reference's lift is a different map (it pulls points towards the middle of the face)
+    Pr = np.stack([r_ref[:N], r_ref[N:2 * N], r_ref[2 * N:]], 1)
+    assert np.max(np.linalg.norm(Pr - P, axis=1)) > 1e-3
+    # corners map to corners
+    v = faces[100]
+    cu = np.concatenate([uvv[v][:, 0], uvv[v][:, 1]])
+    orc.set_lift_mode(1)
+    rc, _, _ = orc.get_r3d(cu)
+    orc.set_lift_mode(0)
+    Pc = np.stack([rc[:3], rc[3:6], rc[6:]], 1)
+    assert min(np.min(np.linalg.norm(x3d - Pc[k], axis=1)) for k in range(3)) < 1e-9
