@@ -249,7 +249,10 @@ def main_ours(args, rank, world, local_rank):
     if slabs and mode != t2d.NEIGH_EUCLID:
         raise SystemExit("multi-GPU slabs support the Euclidean criterion (workloads c4shard / c2)")
     cap = int(Nloc * 1.25) + 65536 if slabs else Nloc      # room for halo copies and migration imbalance
-    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=cap, device=local_rank)
+    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=cap, device=local_rank,
+              lift_mode=t2d.LIFT_BARYCENTRIC if args.lift == "barycentric" else t2d.LIFT_REFERENCE)
+    if args.lift == "barycentric":
+        spec["name"] += ", barycentric lift (extension, not the reference's semantics)"
     if mode == t2d.NEIGH_TABLE:
         kw["table_kind"] = t2d.TABLE_HOPS_FROM_MESH
     ctx = t2d.Context(chart, **kw)
@@ -435,6 +438,8 @@ def main():
     ap.add_argument("--workload", default="c4shard", choices=["c4shard", "c2", "c3"])
     ap.add_argument("--particles-per-gpu", type=int, default=0)
     ap.add_argument("--dtype", default=None, choices=[None, "f32", "f64"])
+    ap.add_argument("--lift", default="reference", choices=["reference", "barycentric"],
+                    help="UV->3-D lift: the reference's distance weights (default, the headline) or the barycentric extension")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline and e2e legs (profiler runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
