@@ -961,13 +961,15 @@ template <typename R> void Engine<R>::comm_phase1()
     prof_mark();
     if (halo_valid_) {
         A_.step = (uint64_t)step_index;
-        Launch<R>::step_euclid(A_, true, stream_);   // cur -> alt
+        Launch<R>::step_euclid(A_, true, stream_);   // cur -> alt; classifies + packs every particle it has just moved
         std::swap(A_.cur, A_.alt);
         launches_++;
+        prof_mark();
+    } else {   // first exchange after an upload: classify + pack the resident state as it is
+        prof_mark();
+        Launch<R>::comm_pack(A_, stream_);
+        launches_++;
     }
-    prof_mark();
-    Launch<R>::comm_pack(A_, stream_);
-    launches_++;
     prof_mark();
 }
 

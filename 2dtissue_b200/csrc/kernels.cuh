@@ -403,6 +403,93 @@ __device__ __forceinline__ void wrap_and_project(const StepArgs<R>& a, Real2<R> 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// slab mode: message layout and the per-particle classification used by the step kernels
+// ---------------------------------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ CommHeader* msg_header(unsigned char* m) { return reinterpret_cast<CommHeader*>(m); }
+template <typename R> __device__ __forceinline__ MigRec<R>* msg_mig(unsigned char* m) { return reinterpret_cast<MigRec<R>*>(m + 16); }
+template <typename R> __device__ __forceinline__ GhostRec<R>* msg_ghost(unsigned char* m, int mig_cap)
+{
+    return reinterpret_cast<GhostRec<R>*>(m + 16 + (size_t)mig_cap * sizeof(MigRec<R>));
+}
+
+// one OWNED particle (slot i of `st`, values passed in registers): where does its new x put it?
+template <typename R>
+__device__ __forceinline__ void slab_classify(const StepArgs<R>& a, const ParticleArrays<R>& st, int i, const Pos3<R>& P,
+                                              const Real2<R>& uvp, const Real2<R>& rd, int4 ax, int color, BlockCounters& bc)
+{
+    const DevComm<R>& cm = a.comm;
+    uint32_t key = KEY_DROP;
+    const R x = P.x;
+    bool keep = true;
+    if (x < cm.lo2 + cm.halo || x >= cm.hi2 - cm.halo) {
+        // landed beyond the adjacent slab, or inside it but within r_max of ITS other cut (seam re-entry / a very
+        // fast particle): the far channel — every rank sees it, so the owner adopts it and whoever has it in its
+        // halo strip takes a copy; no halo copy here (slabs are at least 4 r_max wide)
+        int dest = 0;
+        for (int k = 0; k < cm.world - 1; ++k) dest += (x >= cm.cuts[k]) ? 1 : 0;
+        const int slot = atomicAdd(&msg_header<R>(cm.far_send)->n_mig, 1);
+        if (slot < FAR_CAP) {
+            MigRec<R> r;
+            r.pos = P;
+            r.uv = uvp;
+            r.rdot = rd;
+            r.aux = make_int4(ax.x, ax.y, ax.z, 0);
+            r.color = color;
+            r.pad[0] = dest;
+            r.pad[1] = r.pad[2] = 0;
+            msg_mig<R>(cm.far_send)[slot] = r;
+        } else {
+            bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+        }
+        keep = false;
+    } else if (x < cm.lo || x >= cm.hi) {
+        const int dir = x < cm.lo ? 0 : 1;
+        const int slot = atomicAdd(&msg_header<R>(cm.send[dir])->n_mig, 1);
+        if (slot < cm.mig_cap) {
+            MigRec<R> r;
+            r.pos = P;
+            r.uv = uvp;
+            r.rdot = rd;
+            r.aux = make_int4(ax.x, ax.y, ax.z, 0);
+            r.color = color;
+            r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            msg_mig<R>(cm.send[dir])[slot] = r;
+        } else {
+            bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+        }
+        keep = dir == 0 ? (x >= cm.lo - cm.halo) : (x < cm.hi + cm.halo);
+        if (keep) {   // still within r_max of the cut: our own particles need it as a neighbour — keep a halo copy
+            ax.w = ORIGIN_GHOST;
+            st.aux[i] = ax;
+        }
+    } else {
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            const bool has = dir == 0 ? cm.rank > 0 : cm.rank < cm.world - 1;
+            const bool near = dir == 0 ? (x < cm.lo + cm.halo) : (x >= cm.hi - cm.halo);
+            if (has && near) {
+                const int slot = atomicAdd(&msg_header<R>(cm.send[dir])->n_ghost, 1);
+                if (slot < cm.ghost_cap) {
+                    GhostRec<R> g;
+                    g.pos = P;
+                    g.uv = uvp;
+                    g.id = ax.z;
+                    g.pad = 0;
+                    msg_ghost<R>(cm.send[dir], cm.mig_cap)[slot] = g;
+                } else {
+                    bc.fault |= T2D_FAULT_COMM_OVERFLOW;
+                }
+            }
+        }
+    }
+    if (keep) {
+        key = bucket_key<R>(a, P, ax.x, bc);
+        a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+    }
+    a.key[i] = key;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K3-K5 fused (Euclidean criterion).  d_ij = ||X_i - X_j|| on the 3-D positions of the previous projection.
 // Cell edge = rmax: a neighbour within rmax lies in the 3 x 3 x 3 cells around the particle's own = 3 x 3 rows of
 // 3 x-adjacent cells; a row's 3 cells are ONE contiguous slot range of the sorted state (row_range), so a particle
@@ -435,7 +522,10 @@ template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREAD
     const bool resident = i < resident_count<R>(a);
     const int4 ai = resident ? a.cur.aux[i] : make_int4(0, 0, 0, ORIGIN_DEAD);
     if (resident && ai.w < 0) {   // slab mode: halo copies are read by others, never advanced; they leave at the next sort
-        if (MOVING) a.alt.aux[i] = make_int4(0, -1, ai.z, ORIGIN_DEAD);
+        if (MOVING) {
+            a.alt.aux[i] = make_int4(0, -1, ai.z, ORIGIN_DEAD);
+            a.key[i] = KEY_DROP;
+        }
     } else if (resident) {
         const Pos3<R> Pi = a.cur.pos[i];
         const Real2<R> ui = a.cur.uv[i];
@@ -581,10 +671,12 @@ template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREAD
             a.alt.aux[i] = make_int4(vid, face, ai.z, ai.w);
             a.alt.rdot[i] = rd;
             a.alt.color[i] = color;
-            if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
+            if (!a.comm.on) {
                 const uint32_t key = bucket_key<R>(a, X, vid, bc);
                 a.key[i] = key;
                 a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
+            } else {   // slab mode: stays / migrates / halo copy, messages, key
+                slab_classify<R>(a, a.alt, i, X, p, rd, make_int4(vid, face, ai.z, ai.w), color, bc);
             }
         } else {   // t2d_forces: report without moving
             Real2<R> Fv = {fx, fy};
@@ -660,7 +752,10 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
     const bool resident = i < resident_count<R>(a);
     const int4 ai = resident ? a.cur.aux[i] : make_int4(0, 0, 0, ORIGIN_DEAD);
     const bool live = resident && ai.w >= 0;   // slab mode: halo copies are read by others, never advanced
-    if (MOVING && resident && !live) a.alt.aux[i] = make_int4(0, -1, ai.z, ORIGIN_DEAD);
+    if (MOVING && resident && !live) {
+        a.alt.aux[i] = make_int4(0, -1, ai.z, ORIGIN_DEAD);
+        a.key[i] = KEY_DROP;
+    }
 
     unsigned npairs = 0, nties = 0;
     Real2<R> ui = {0.0f, 0.0f}, rd = {0.0f, 0.0f}, p = {0.0f, 0.0f};
@@ -819,7 +914,12 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
             a.alt.aux[i] = make_int4(vid, f, ai.z, ai.w);
             a.alt.rdot[i] = rd;
             a.alt.color[i] = color;
-            if (!a.comm.on) {   // slab mode: k_comm_pack classifies the particle and emits the key
+            if (a.comm.on) {   // slab mode: stays / migrates / halo copy, messages, key
+                BlockCounters sbc;
+                slab_classify<R>(a, a.alt, i, X, p, rd, make_int4(vid, f, ai.z, ai.w), color, sbc);
+                if (sbc.fault) atomicOr(&a.counters->fault, sbc.fault);
+                if (sbc.cell_fb) atomicAdd(&a.counters->cell_fallbacks, sbc.cell_fb);
+            } else {
                 int c[3];
                 cell_coords<R>(a.vox, X, c);
                 int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
@@ -1073,92 +1173,18 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
 // remains resident.  A migrant still within r_max of the cut stays behind as a halo copy, so no second
 // exchange round is needed.
 // ---------------------------------------------------------------------------------------------------
-template <typename R> __device__ __forceinline__ CommHeader* msg_header(unsigned char* m) { return reinterpret_cast<CommHeader*>(m); }
-template <typename R> __device__ __forceinline__ MigRec<R>* msg_mig(unsigned char* m) { return reinterpret_cast<MigRec<R>*>(m + 16); }
-template <typename R> __device__ __forceinline__ GhostRec<R>* msg_ghost(unsigned char* m, int mig_cap)
-{
-    return reinterpret_cast<GhostRec<R>*>(m + 16 + (size_t)mig_cap * sizeof(MigRec<R>));
-}
-
+// stand-alone pass over the resident state (the first exchange after an upload; during stepping the step kernels
+// classify each particle themselves, right after computing its new position)
 template <typename R> __global__ void __launch_bounds__(256) k_comm_pack(StepArgs<R> a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     BlockCounters bc;
-    const DevComm<R>& cm = a.comm;
-    if (i < cm.state->n) {
-        int4 ax = a.cur.aux[i];
-        uint32_t key = KEY_DROP;
-        if (ax.w >= 0) {
-            const Pos3<R> P = a.cur.pos[i];
-            const R x = P.x;
-            bool keep = true;
-            if (x < cm.lo2 + cm.halo || x >= cm.hi2 - cm.halo) {
-                // landed beyond the adjacent slab, or inside it but within r_max of ITS other cut (seam re-entry / a very
-                // fast particle): the far channel — every rank sees it, so the owner adopts it and whoever has it in its
-                // halo strip takes a copy; no halo copy here (slabs are at least 4 r_max wide)
-                int dest = 0;
-                for (int k = 0; k < cm.world - 1; ++k) dest += (x >= cm.cuts[k]) ? 1 : 0;
-                const int slot = atomicAdd(&msg_header<R>(cm.far_send)->n_mig, 1);
-                if (slot < FAR_CAP) {
-                    MigRec<R> r;
-                    r.pos = P;
-                    r.uv = a.cur.uv[i];
-                    r.rdot = a.cur.rdot[i];
-                    r.aux = make_int4(ax.x, ax.y, ax.z, 0);
-                    r.color = a.cur.color[i];
-                    r.pad[0] = dest;
-                    r.pad[1] = r.pad[2] = 0;
-                    msg_mig<R>(cm.far_send)[slot] = r;
-                } else {
-                    bc.fault |= T2D_FAULT_COMM_OVERFLOW;
-                }
-                keep = false;
-            } else if (x < cm.lo || x >= cm.hi) {
-                const int dir = x < cm.lo ? 0 : 1;
-                const int slot = atomicAdd(&msg_header<R>(cm.send[dir])->n_mig, 1);
-                if (slot < cm.mig_cap) {
-                    MigRec<R> r;
-                    r.pos = P;
-                    r.uv = a.cur.uv[i];
-                    r.rdot = a.cur.rdot[i];
-                    r.aux = make_int4(ax.x, ax.y, ax.z, 0);
-                    r.color = a.cur.color[i];
-                    r.pad[0] = r.pad[1] = r.pad[2] = 0;
-                    msg_mig<R>(cm.send[dir])[slot] = r;
-                } else {
-                    bc.fault |= T2D_FAULT_COMM_OVERFLOW;
-                }
-                keep = dir == 0 ? (x >= cm.lo - cm.halo) : (x < cm.hi + cm.halo);
-                if (keep) {   // still within r_max of the cut: our own particles need it as a neighbour — keep a halo copy
-                    ax.w = ORIGIN_GHOST;
-                    a.cur.aux[i] = ax;
-                }
-            } else {
-#pragma unroll
-                for (int dir = 0; dir < 2; ++dir) {
-                    const bool has = dir == 0 ? cm.rank > 0 : cm.rank < cm.world - 1;
-                    const bool near = dir == 0 ? (x < cm.lo + cm.halo) : (x >= cm.hi - cm.halo);
-                    if (has && near) {
-                        const int slot = atomicAdd(&msg_header<R>(cm.send[dir])->n_ghost, 1);
-                        if (slot < cm.ghost_cap) {
-                            GhostRec<R> g;
-                            g.pos = P;
-                            g.uv = a.cur.uv[i];
-                            g.id = ax.z;
-                            g.pad = 0;
-                            msg_ghost<R>(cm.send[dir], cm.mig_cap)[slot] = g;
-                        } else {
-                            bc.fault |= T2D_FAULT_COMM_OVERFLOW;
-                        }
-                    }
-                }
-            }
-            if (keep) {
-                key = bucket_key<R>(a, P, ax.x, bc);
-                a.rank[i] = (uint32_t)atomicAdd(&a.count[key], 1);
-            }
-        }
-        a.key[i] = key;
+    if (i < a.comm.state->n) {
+        const int4 ax = a.cur.aux[i];
+        if (ax.w >= 0)
+            slab_classify<R>(a, a.cur, i, a.cur.pos[i], a.cur.uv[i], a.cur.rdot[i], ax, a.cur.color[i], bc);
+        else
+            a.key[i] = KEY_DROP;   // halo copy of the previous step
     }
     flush_counters(bc, a.counters);
 }
