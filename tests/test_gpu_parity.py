@@ -482,3 +482,34 @@ def test_barycentric_lift_vs_oracle(t2d, chart, oracle):
         assert c32.step(3) == 0
     finally:
         oracle.set_lift_mode(0)
+
+
+def test_coincident_in_3d_but_not_in_uv(t2d, chart, oracle):
+    """ForceHelper.cpp:59-62: d == 0 -> d := 0.001.  Two particles can share a 3-D position while their uv differ (in
+    fp32 this happens inside dense clumps); 1/d must then be 1000, not unbounded — a clamp instead of the rule once made
+    the bench blow up at random.  State injected through t2d_set_state, compared with the oracle."""
+    N, sigma = 64, 0.05
+    uv, n = t2d.seed_particles(N, seed=77)
+    r3d, vid, _ = oracle.get_r3d(uv)
+    r3d, vid = r3d.copy(), vid.copy()
+    for k in range(3):                       # particles 1 and 2 sit exactly on particle 0 in 3-D; their uv stay distinct
+        r3d[k * N + 1] = r3d[k * N + 2] = r3d[k * N + 0]
+    o = oracle.step(uv, n, vid, r3d, 0.1, 1.0, sigma, 0.001, mode=1)
+    for prec, tol in ((t2d.PRECISION_FP64, 0.0), (t2d.PRECISION_FP32, 2e-3)):
+        ctx = t2d.Context(chart, v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=t2d.NEIGH_EUCLID, precision=prec,
+                          capacity=N)
+        ctx.set_state(uv, n, vid, r3d)
+        F, nh, col = ctx.forces()
+        assert np.all(np.isfinite(F))
+        assert np.array_equal(col, o["color"])            # 0 != d: coincident particles are not counted
+        ctx.set_state(uv, n, vid, r3d)
+        assert ctx.step(1) == o["fault"]
+        g = ctx.download()
+        speed = np.hypot(o["rdot"][:N], o["rdot"][N:])
+        assert speed[0] > 1.0                              # the rule really acted: |F| ~ 1000 * |uv difference|
+        if tol == 0.0:
+            assert np.array_equal(g["rdot"], o["rdot"])
+        else:
+            sc = np.maximum(np.concatenate([speed, speed]), 1.0)
+            assert np.max(np.abs(g["rdot"] - o["rdot"]) / sc) <= tol
+        ctx.close()
