@@ -260,6 +260,42 @@ def slab_of(x, cuts):
     return np.searchsorted(np.asarray(cuts, dtype=np.float64), np.asarray(x, dtype=np.float64), side="right").astype(np.int32)
 
 
+def route_after_step(x, cuts, rank, halo):
+    """Host-side restatement of `slab_classify` (csrc/kernels.cuh): where the particles OWNED by `rank` go after a step,
+    from their new 3-D x.  Returns boolean masks over x:
+        stay                      keeps its owner
+        to_left / to_right        migrates through the message to slab-1 / slab+1
+        keep_halo                 migrant that stays behind as a halo copy (still within `halo` of the cut it crossed)
+        halo_left / halo_right    stays, and a halo copy goes to slab-1 / slab+1
+        far                       goes into the far message every rank receives (landed beyond the adjacent slab, or
+                                  inside it but within `halo` of its other cut)
+    and dest = the slab that owns the new x.  Slabs must be at least 4 halo wide (t2d_comm_init checks it)."""
+    x = np.asarray(x, dtype=np.float64)
+    cuts = np.asarray(cuts, dtype=np.float64)
+    world = len(cuts) + 1
+    cut = lambda k: -np.inf if k < 0 else (np.inf if k >= world - 1 else cuts[k])
+    lo, hi, lo2, hi2 = cut(rank - 1), cut(rank), cut(rank - 2), cut(rank + 1)
+    far = (x < lo2 + halo) | (x >= hi2 - halo)
+    left = ~far & (x < lo)
+    right = ~far & (x >= hi)
+    keep_halo = (left & (x >= lo - halo)) | (right & (x < hi + halo))
+    stay = ~far & ~left & ~right
+    return dict(stay=stay, to_left=left, to_right=right, keep_halo=keep_halo, far=far,
+                halo_left=stay & (rank > 0) & (x < lo + halo), halo_right=stay & (rank < world - 1) & (x >= hi - halo),
+                dest=slab_of(x, cuts))
+
+
+def far_receive(x, dest, cuts, rank, halo):
+    """What `rank` does with the far records of the other ranks (k_comm_unpack_far): (adopt, halo_copy) masks."""
+    x = np.asarray(x, dtype=np.float64)
+    cuts = np.asarray(cuts, dtype=np.float64)
+    world = len(cuts) + 1
+    lo = -np.inf if rank == 0 else cuts[rank - 1]
+    hi = np.inf if rank == world - 1 else cuts[rank]
+    mine = np.asarray(dest) == rank
+    return mine, ~mine & (x >= lo - halo) & (x < hi + halo)
+
+
 def partition_by_slab(state, cuts, rank):
     """The sub-state (with global ids) that `rank` owns.  state: dict(uv, n, vid, r3d) in the reference's layouts."""
     N = state["n"].size
