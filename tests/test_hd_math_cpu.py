@@ -92,3 +92,28 @@ def test_mean_angle_correctly_rounded_matches_glibc_pipeline(hd_lib):
         assert bad == 0
         if family < 2:
             assert ties.value > 0.5 * sets.value
+
+
+def test_fast_path_pair_algebra_matches_the_reference_formula(oracle_mod):
+    """The fp32 step kernel evaluates F_ij / d as ONE FMA on 1/d:  (-k)/d + k/(2 sigma)  (k_step_euclid_fast, pair_term).
+    Same number as the reference's  [-k (2 sigma - d) / (2 sigma)] / d  (ForceHelper.cpp:84-104, via the oracle's
+    t2do_repulsive_adhesion), including the d == 0 -> 0.001 rule (ForceHelper.cpp:59-62), to fp32 accuracy."""
+    L = oracle_mod.lib()
+    rng = np.random.default_rng(4)
+    k, sigma = 1.0, 0.05
+    d = np.concatenate([rng.random(2000) * 2 * sigma, [1e-7, 1e-5, 0.001, 2 * sigma * (1 - 1e-7)]])
+    duv = rng.normal(size=(d.size, 2)) * 1e-3
+    for dist, (ux, uy) in zip(d, duv):
+        out = (C.c_double * 2)()
+        # oracle: F_ij * dist_v / dist  with dist_v = (ux, uy)
+        L.t2do_repulsive_adhesion(C.c_double(k), C.c_double(sigma), C.c_double(dist), C.c_double(1.0), C.c_double(0.75),
+                                  C.c_double(ux), C.c_double(uy), out)
+        rinv = np.float32(1.0) / np.float32(dist)
+        g = np.float32(rinv * np.float32(-k) + np.float32(k / (2 * sigma)))
+        fx, fy = float(g * np.float32(ux)), float(g * np.float32(uy))
+        scale = max(abs(out[0]), abs(out[1]), 1e-12)
+        assert abs(fx - out[0]) <= 2e-5 * scale + 1e-9 and abs(fy - out[1]) <= 2e-5 * scale + 1e-9
+    # d == 0: the rule gives 1/d = 1000
+    g0 = np.float32(1000.0) * np.float32(-k) + np.float32(k / (2 * sigma))
+    ref = (-k * (2 * sigma - 0.001) / (2 * sigma)) / 0.001
+    assert abs(float(g0) - ref) <= 1e-5 * abs(ref)
