@@ -35,6 +35,3 @@ print("total warp-instr %.0f  samples %.0f  thread-instr %.0f  avg lanes %.1f" %
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     fn, tx = text(*k)
     print("%5.1f%% inst %5.1f%% smp lanes %4.1f  %s:%d  %s" % (100*a[1]/ti, 100*a[0]/ts, a[2]/max(a[1],1), fn, k[1], tx))
-# category totals for k_step_euclid (line ranges of kernels.cuh / hd_math.cuh at the time of the capture)
-if '--cats' in sys.argv:
-    pass
