@@ -21,13 +21,18 @@ namespace t2d {
 // small device helpers
 // ---------------------------------------------------------------------------------------------------
 // (cos, sin) of an integer-degree heading exactly as the reference's libm call sees it (host-built table)
+// outside the host-built table: CUDA libm (may differ from glibc in the last ulp) — counted by the caller.  Out of line:
+// double-precision cos + sin are several hundred instructions and this never runs in practice.
+static __device__ __noinline__ double2 trig_slow(int n)
+{
+    double r = (double)n * DEG_TO_RAD_D;
+    return make_double2(cos(r), sin(r));
+}
 __device__ __forceinline__ double2 trig_lookup(const double2* __restrict__ tab, int n, unsigned long long& fb)
 {
     if (n >= TRIG_MIN && n <= TRIG_MAX) return __ldg(&tab[n - TRIG_MIN]);
-    // outside the host-built table: CUDA libm (may differ from glibc in the last ulp) — counted
-    double r = (double)n * DEG_TO_RAD_D;
     fb++;
-    return make_double2(cos(r), sin(r));
+    return trig_slow(n);
 }
 
 template <typename R> __device__ __forceinline__ R dev_floor(R v);
@@ -127,6 +132,32 @@ template <typename R> __device__ __forceinline__ void row_range(const StepArgs<R
     if (hi > lo) {
         b = a.start[lo];
         e = a.start[hi];
+    }
+}
+
+// the same, also returning the compact index of the run's first cell (the tiled kernel looks its staged copy up by it)
+template <typename R>
+__device__ __forceinline__ void row_range_lo(const StepArgs<R>& a, int x0, int y, int z, int& b, int& e, int& clo)
+{
+    const DevVox<R>& vx = a.vox;
+    b = e = 0;
+    clo = 0;
+    if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz || x0 < 1 || x0 > vx.ncx - 2) return;
+    const int xl = x0 - 1, xh = x0 + 2;
+    const uint2* row = vx.words + ((size_t)z * vx.ncy + y) * vx.nwx;
+    const uint2 e0 = __ldg(row + (xl >> 5));
+    const int lo = (int)e0.y + __popc(e0.x & ((1u << (xl & 31)) - 1u));
+    int hi;
+    if ((xh >> 5) == (xl >> 5)) {
+        hi = (int)e0.y + __popc(e0.x & ((1u << (xh & 31)) - 1u));
+    } else {
+        const uint2 e1 = __ldg(row + (xh >> 5));
+        hi = (int)e1.y + __popc(e1.x & ((1u << (xh & 31)) - 1u));
+    }
+    if (hi > lo) {
+        b = a.start[lo];
+        e = a.start[hi];
+        clo = lo;
     }
 }
 
@@ -682,7 +713,7 @@ template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREAD
             Real2<R> Fv = {fx, fy};
             a.F[i] = Fv;
             a.new_heading[i] = n_new;
-            a.cur.color[i] = color;
+            a.alt.color[i] = color;
         }
     }
     flush_counters(bc, a.counters);
@@ -723,16 +754,151 @@ struct PairAcc {
 // (ForceHelper.cpp:84-104).  d = 0 -> d := 0.001 (ForceHelper.cpp:59-62): the particle itself (ui - uj = 0, no force)
 // or one whose 3-D position coincides with it in fp32 while its uv does not — common inside the dense clumps the
 // lift produces, so the rule matters: without it 1/d is unbounded and a single pair throws both particles off the chart.
-__device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const Real2<float>* __restrict__ uv, int j, float d2,
-                                          const Real2<float>& ui, float g1, float g0, PairAcc& acc)
+__device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const double2* __restrict__ trig,
+                                          const Real2<float>* __restrict__ uv, int j, float heading_j, float d2,
+                                          const Real2<float>& ui, float g1, float g0, PairAcc& acc, unsigned long long& trig_fb)
 {
-    const double2 t = cs[j];
+    // (cos, sin) of the neighbour's heading: the per-particle array the sort makes (legacy layout), else the host-libm table
+    const double2 t = cs ? cs[j] : trig_lookup(trig, (int)heading_j, trig_fb);
     const Real2<float> uj = uv[j];
     acc.mx += t.x;
     acc.my += t.y;
     const float g = fmaf(d2 == 0.0f ? 1000.0f : rsqrtf(d2), g1, g0);
     acc.fx = fmaf(g, ui.x - uj.x, acc.fx);
     acc.fy = fmaf(g, ui.y - uj.y, acc.fy);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-particle tail of the fp32 fast path, shared by k_step_euclid_fast and k_step_euclid_tiled: speed and velocity
+// (Locomotion.cpp:71-81), heading after alignment (+ noise), Euler step (Locomotion.cpp:84), seam re-entry, validation,
+// UV point location (previous-face hint, else first containing face of the grid cell, else the distance arg-min),
+// lift, next bucket key / slab classification.  `own` = (cos, sin) of the particle's OLD heading.
+// ---------------------------------------------------------------------------------------------------
+// rare paths of the fast epilogue, out of line (code size: the hot loop shares the instruction cache with them)
+// (arguments and results by value: a reference into the caller's registers or into the kernel's parameter block would
+// force them into local memory)
+struct SeamResult { float px, py; int n, wraps, cap; };
+static __device__ __noinline__ SeamResult seam_reentry_f32(float oldx, float oldy, float px, float py, int n)
+{
+    SeamResult r;
+    int wraps = 0;
+    r.cap = seam_reentry<float>(oldx, oldy, px, py, n, wraps) ? 1 : 0;
+    r.px = px;
+    r.py = py;
+    r.n = n;
+    r.wraps = wraps;
+    return r;
+}
+// returns the face; bit 31 set = the cell list did not cover the point and all faces were scanned (counted by the caller)
+static __device__ __noinline__ int locate_face_argmin_f32(int V, int F, int G, const TriUV<float>* tri, const int* gstart,
+                                                          const int* gfaces, float px, float py)
+{
+    DevMesh<float> m;
+    m.V = V;
+    m.F = F;
+    m.G = G;
+    m.tri = tri;
+    m.gstart = gstart;
+    m.gfaces = gfaces;
+    BlockCounters lc;
+    const int f = locate_face<float>(m, px, py, lc);
+    return lc.loc_fb ? (f | (int)0x80000000) : f;
+}
+
+template <bool MOVING>
+__device__ __forceinline__ void fast_epilogue(const StepArgs<float>& a, int i, const int4 ai, const Real2<float> ui, const double2 own,
+                                              const PairAcc& acc, int color, int hits, unsigned& npairs, unsigned& nties)
+{
+    typedef float R;
+    const float fx = acc.fx, fy = acc.fy;
+    npairs = hits > 0 ? (unsigned)(hits - 1) : 0u;   // without itself
+    const float absF = sqrtf(fx * fx + fy * fy) + a.v0;
+    Real2<R> rd = {(float)own.x * absF, (float)own.y * absF};
+    int n_new;
+    {   // the sums are doubles on this path too (see heading_from_sum)
+        BlockCounters hc;
+        n_new = heading_from_sum<R>(a, acc.mx, acc.my, (uint32_t)ai.z, hc);
+        nties = (unsigned)hc.ties_trunc;
+    }
+    if (!MOVING) {   // t2d_forces: report without moving (colour into the scratch side of the double buffer)
+        Real2<R> Fv = {fx, fy};
+        a.F[i] = Fv;
+        a.new_heading[i] = n_new;
+        a.alt.color[i] = color;
+        return;
+    }
+    Real2<R> p = {ui.x + rd.x * a.step_size, ui.y + rd.y * a.step_size};   // Locomotion.cpp:84
+    Real2<R> old = ui;
+    int wraps = 0;
+    bool cap = false;
+    if (!inside_square<R>(p.x, p.y)) {   // ~1 particle in 10^3 per step
+        const SeamResult sr = seam_reentry_f32(old.x, old.y, p.x, p.y, n_new);
+        p.x = sr.px;
+        p.y = sr.py;
+        n_new = sr.n;
+        wraps = sr.wraps;
+        cap = sr.cap != 0;
+    }
+    unsigned fault = 0;
+    if (wraps) atomicAdd(&a.counters->wraps, (unsigned long long)wraps);
+    if (cap) {
+        atomicAdd(&a.counters->wrap_cap_hits, 1ull);
+        fault |= T2D_FAULT_WRAP_CAP;
+    }
+    if (!inside_square<R>(p.x, p.y)) {   // Validation::error_lost_particles
+        atomicAdd(&a.counters->lost, 1ull);
+        fault |= T2D_FAULT_LOST;
+    }
+    if (!isfinite(p.x) || !isfinite(p.y)) {   // Validation::error_invalid_values
+        atomicAdd(&a.counters->nonfinite, 1ull);
+        fault |= T2D_FAULT_NONFINITE;
+    }
+    if (fault) atomicOr(&a.counters->fault, fault);
+    const int hint = wraps == 0 ? ai.y : -1;
+    int f = hint;
+    bool need_locate = true;
+    if (hint >= 0) need_locate = !hint_contains(a.mesh.tri[hint], p.x, p.y);
+    if (need_locate) {
+        // the particle left its previous face (about 1 in 7 per step): first face of its grid cell that contains it
+        f = locate_face_contains(a.mesh, p.x, p.y);
+        if (f < 0) {   // within rounding of an edge (or outside every listed face): the reference's arg-min over distances
+            f = locate_face_argmin_f32(a.mesh.V, a.mesh.F, a.mesh.G, a.mesh.tri, a.mesh.gstart, a.mesh.gfaces, p.x, p.y);
+            if (f < 0) {
+                f &= 0x7fffffff;
+                atomicAdd(&a.counters->locate_fallbacks, 1ull);
+            }
+        }
+    }
+    const TriUV<R> t = a.mesh.tri[f];
+    const int4 tv = a.mesh.tri_vid[f];
+    const Pos3<R> A = a.mesh.x3d[tv.x], B = a.mesh.x3d[tv.y], C = a.mesh.x3d[tv.z];
+    const R Av[3] = {A.x, A.y, A.z}, Bv[3] = {B.x, B.y, B.z}, Cv[3] = {C.x, C.y, C.z};
+    R Xv[3];
+    const int which = lift_to_3d<R>(p.x, p.y, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv,
+                                    a.mesh.lift_mode == T2D_LIFT_BARYCENTRIC);
+    const int vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
+    const Pos3<R> X = {Xv[0], Xv[1], Xv[2], (R)n_new};
+    a.alt.pos[i] = X;
+    a.alt.uv[i] = p;
+    a.alt.aux[i] = make_int4(vid, f, ai.z, ai.w);
+    a.alt.rdot[i] = rd;
+    a.alt.color[i] = color;
+    if (a.comm.on) {   // slab mode: stays / migrates / halo copy, messages, key
+        BlockCounters sbc;
+        slab_classify<R>(a, a.alt, i, X, p, rd, make_int4(vid, f, ai.z, ai.w), color, sbc);
+        if (sbc.fault) atomicOr(&a.counters->fault, sbc.fault);
+        if (sbc.cell_fb) atomicAdd(&a.counters->cell_fallbacks, sbc.cell_fb);
+    } else {
+        int c[3];
+        cell_coords<R>(a.vox, X, c);
+        int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
+        if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket
+            atomicAdd(&a.counters->cell_fallbacks, 1ull);
+            idx = a.vox.M;
+        }
+        a.key[i] = (uint32_t)idx;
+        a.rank[i] = (uint32_t)atomicAdd(&a.count[idx], 1);
+    }
 }
 
 #ifndef T2D_UNROLL
@@ -758,10 +924,8 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
     }
 
     unsigned npairs = 0, nties = 0;
-    Real2<R> ui = {0.0f, 0.0f}, rd = {0.0f, 0.0f}, p = {0.0f, 0.0f};
-    int n_new = 0, color = 0, hint = -1;
-    bool need_locate = false;
-    float fx = 0.0f, fy = 0.0f;
+    Real2<R> ui = {0.0f, 0.0f};
+    int color = 0;
 
     const float r2s = a.two_sigma * a.two_sigma, r2c = a.color_r * a.color_r;
     const float g1 = -a.k, g0 = a.k / a.two_sigma;
@@ -769,6 +933,10 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
     const double2* __restrict__ cs = a.cur.cs;
     const Real2<R>* __restrict__ uv = a.cur.uv;
     const unsigned r2c_bits = __float_as_uint(r2c);
+    const unsigned tie_s_lo = __float_as_uint(r2s) - 9u, tie_c_lo = r2c_bits - 9u;   // within 8 ulps of a cutoff
+    const bool count_ties = a.count_ties != 0;
+    unsigned ncut = 0;
+    unsigned long long trig_fb = 0;
     PairAcc acc;
     int hits = 0;
 
@@ -836,113 +1004,33 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
                 asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tadd.u32 t, %1, -1;\n\tsetp.lt.u32 p, t, %2;\n\t@p add.s32 %0, %0, 1;\n\t}"
                     : "+r"(color)
                     : "r"(__float_as_uint(d2)), "r"(r2c_bits));
+                if (count_ties) {   // near-cutoff candidates: the "logged ties" of the parity bar (see step_tiled.cuh cand_loop)
+                    const unsigned bm1 = __float_as_uint(d2) - 1u;
+                    if ((bm1 - tie_s_lo) <= 16u || (bm1 - tie_c_lo) <= 16u) ncut++;
+                }
                 if (d2 < r2s) {
-                    pair_term(cs, uv, jb + t, d2, ui, g1, g0, acc);
+                    pair_term(cs, a.trig_d, uv, jb + t, Pj.w, d2, ui, g1, g0, acc, trig_fb);
                     hits++;
                 }
             }
         }
     }
 
+    __syncwarp();   // reconverge: lanes leave the candidate loops at different times, the tail below is the same for all
     if (live) {
-        const double2 own = a.cur.cs[i];
-        fx = acc.fx;
-        fy = acc.fy;
-        const double mx = acc.mx, my = acc.my;
-        npairs = hits > 0 ? (unsigned)(hits - 1) : 0u;   // without itself
-
-        // speed and velocity (Locomotion.cpp:71-81): own heading's unit vector from the cs array
-        const float absF = sqrtf(fx * fx + fy * fy) + a.v0;
-        rd.x = (float)own.x * absF;
-        rd.y = (float)own.y * absF;
-        // heading after alignment (+ noise); the sums are doubles on this path too (see heading_from_sum)
-        {
-            BlockCounters hc;
-            n_new = heading_from_sum<R>(a, mx, my, (uint32_t)ai.z, hc);
-            nties = (unsigned)hc.ties_trunc;
-        }
-        if (MOVING) {
-            p.x = ui.x + rd.x * a.step_size;   // Locomotion.cpp:84
-            p.y = ui.y + rd.y * a.step_size;
-            Real2<R> old = ui;
-            int wraps = 0;
-            const bool cap = seam_reentry<R>(old.x, old.y, p.x, p.y, n_new, wraps);
-            unsigned fault = 0;
-            if (wraps) atomicAdd(&a.counters->wraps, (unsigned long long)wraps);
-            if (cap) {
-                atomicAdd(&a.counters->wrap_cap_hits, 1ull);
-                fault |= T2D_FAULT_WRAP_CAP;
-            }
-            if (!inside_square<R>(p.x, p.y)) {   // Validation::error_lost_particles
-                atomicAdd(&a.counters->lost, 1ull);
-                fault |= T2D_FAULT_LOST;
-            }
-            if (!isfinite(p.x) || !isfinite(p.y)) {   // Validation::error_invalid_values
-                atomicAdd(&a.counters->nonfinite, 1ull);
-                fault |= T2D_FAULT_NONFINITE;
-            }
-            if (fault) atomicOr(&a.counters->fault, fault);
-            hint = wraps == 0 ? ai.y : -1;
-            need_locate = true;
-            if (hint >= 0) need_locate = !hint_contains(a.mesh.tri[hint], p.x, p.y);
-        }
-    }
-
-    if (MOVING) {
-        if (live) {
-            int f = hint;
-            if (need_locate) {
-                // the particle left its previous face (about 1 in 7 per step): first face of its grid cell that contains it
-                f = locate_face_contains(a.mesh, p.x, p.y);
-                if (f < 0) {   // within rounding of an edge (or outside every listed face): the reference's arg-min over distances
-                    BlockCounters lc;
-                    f = locate_face<R>(a.mesh, p.x, p.y, lc);
-                    if (lc.loc_fb) atomicAdd(&a.counters->locate_fallbacks, lc.loc_fb);
-                }
-            }
-            const TriUV<R> t = a.mesh.tri[f];
-            const int4 tv = a.mesh.tri_vid[f];
-            const Pos3<R> A = a.mesh.x3d[tv.x], B = a.mesh.x3d[tv.y], C = a.mesh.x3d[tv.z];
-            const R Av[3] = {A.x, A.y, A.z}, Bv[3] = {B.x, B.y, B.z}, Cv[3] = {C.x, C.y, C.z};
-            R Xv[3];
-            const int which = lift_to_3d<R>(p.x, p.y, t.ax, t.ay, t.bx, t.by, t.cx, t.cy, Av, Bv, Cv, Xv,
-                                            a.mesh.lift_mode == T2D_LIFT_BARYCENTRIC);
-            const int vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
-            const Pos3<R> X = {Xv[0], Xv[1], Xv[2], (R)n_new};
-            a.alt.pos[i] = X;
-            a.alt.uv[i] = p;
-            a.alt.aux[i] = make_int4(vid, f, ai.z, ai.w);
-            a.alt.rdot[i] = rd;
-            a.alt.color[i] = color;
-            if (a.comm.on) {   // slab mode: stays / migrates / halo copy, messages, key
-                BlockCounters sbc;
-                slab_classify<R>(a, a.alt, i, X, p, rd, make_int4(vid, f, ai.z, ai.w), color, sbc);
-                if (sbc.fault) atomicOr(&a.counters->fault, sbc.fault);
-                if (sbc.cell_fb) atomicAdd(&a.counters->cell_fallbacks, sbc.cell_fb);
-            } else {
-                int c[3];
-                cell_coords<R>(a.vox, X, c);
-                int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
-                if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket
-                    atomicAdd(&a.counters->cell_fallbacks, 1ull);
-                    idx = a.vox.M;
-                }
-                a.key[i] = (uint32_t)idx;
-                a.rank[i] = (uint32_t)atomicAdd(&a.count[idx], 1);
-            }
-        }
-    } else if (live) {   // t2d_forces: report without moving
-        Real2<R> Fv = {fx, fy};
-        a.F[i] = Fv;
-        a.new_heading[i] = n_new;
-        a.cur.color[i] = color;
+        const double2 own = cs ? cs[i] : trig_lookup(a.trig_d, (int)a.cur.pos[i].w, trig_fb);
+        fast_epilogue<MOVING>(a, i, ai, ui, own, acc, color, hits, npairs, nties);
     }
     // diagnostic counters: one atomic per warp
     npairs = __reduce_add_sync(0xffffffffu, npairs);
     nties = __reduce_add_sync(0xffffffffu, nties);
+    ncut = __reduce_add_sync(0xffffffffu, ncut);
+    const unsigned fbw = __reduce_add_sync(0xffffffffu, (unsigned)trig_fb);
     if ((tid & 31) == 0) {
         if (npairs) atomicAdd(&a.counters->pairs_in_range, (unsigned long long)npairs);
         if (nties) atomicAdd(&a.counters->ties_trunc, (unsigned long long)nties);
+        if (ncut) atomicAdd(&a.counters->ties_cutoff, (unsigned long long)ncut);
+        if (fbw) atomicAdd(&a.counters->trig_fallbacks, (unsigned long long)fbw);
     }
 }
 

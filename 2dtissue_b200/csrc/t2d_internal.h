@@ -54,6 +54,20 @@ template <typename R> struct DevVox {
     R inv_cell = 0;
 };
 
+// Static tiling of the sparse row index for the staged fast path (k_step_euclid_tiled).  The set of surface cells never
+// changes, so which cells a cell's 3 x 3 x 3 neighbourhood touches is known when the index is built: compact cells are cut
+// into tiles of `tile_cells` consecutive indices (= consecutive slots of the sorted state), and for every tile the host
+// merges the compact-index runs its cells can see into at most TILE_IMAX intervals [lo, hi).  At run time an interval is
+// the slot range [start[lo], start[hi]) — one contiguous piece of pos[] / uv[] — which a CTA stages into shared memory
+// with cp.async.bulk before its threads walk their candidate ranges there.
+struct DevTiles {
+    int ntiles = 0;                // tiles over compact cells [0, M); tile number `ntiles` is the overflow bucket
+    int tile_cells = 0;
+    const int* istart = nullptr;   // [ntiles + 1] CSR into ints; an empty list = tile not staged (too many intervals)
+    const int2* ints = nullptr;    // merged intervals, ascending lo
+    int* queue = nullptr;          // dynamic tile counter, zeroed before every launch
+};
+
 // ---- particle state, SoA, in "slot" order (sorted by bucket key) --------------------------------------
 template <typename R> struct alignas(2 * sizeof(R)) Real2 { R x, y; };
 template <typename R> struct ParticleArrays {
@@ -133,6 +147,7 @@ template <typename R> struct StepArgs {
     DevMesh<R> mesh;
     DevCSR csr;
     DevVox<R> vox;
+    DevTiles tiles;
     DevComm<R> comm;
     // parameters
     R v0, k, two_sigma, color_r, step_size;
@@ -141,6 +156,7 @@ template <typename R> struct StepArgs {
     uint64_t seed, step;
     int mode;
     int write_F;
+    int count_ties = 1;            // fp32 fast path: log candidates within 8 ulps of a cutoff in ties_cutoff
     int* work_counter = nullptr;   // dynamic bucket queue for the table-mode kernel
 };
 
@@ -151,6 +167,7 @@ template <typename R> struct Launch {
     static void bin(const StepArgs<R>& a, cudaStream_t s);                      // key + rank + histogram of `cur`
     static void scatter(const StepArgs<R>& a, cudaStream_t s);                  // cur -> alt in bucket order
     static void step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s); // stages 2-5 fused, cur -> alt (+ next keys)
+    static bool step_euclid_tiled(const StepArgs<R>& a, int sm_count, cudaStream_t s);   // fp32 only: staged tiles; false = not available
     static void neigh_table(const StepArgs<R>& a, cudaStream_t s, int sm_count);
     static void wrap_project(const StepArgs<R>& a, cudaStream_t s);             // table mode stages 4b-5, in place (+ next keys)
     static void project_only(const StepArgs<R>& a, cudaStream_t s);             // initial projection (get_r3d)
