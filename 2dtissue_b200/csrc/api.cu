@@ -215,11 +215,8 @@ template <typename R> class Engine : public EngineBase {
     DevBuf<double2> d_trig_d_;
     DevBuf<CrEntry> d_cr_;
     DevBuf<uint2> d_vox_words_;
-    DevBuf<int> d_tile_istart_;
-    DevBuf<int2> d_tile_ints_;
-    bool use_tiled_ = false;       // fp32 Euclid: the staged-tile step kernel (step_tiled.cuh); T2D_STEP=legacy switches it off
-    void build_tiles(const std::vector<uint2>& words, const std::vector<std::pair<uint64_t, size_t>>& order, const int nc[3],
-                     int nwx, int M);
+    DevBuf<int2> d_nbr_;
+    bool use_fast2_ = false;       // fp32 Euclid: k_step_fast2 (step_fast2.cuh) on 32-byte records; T2D_STEP=legacy switches it off
     DevBuf<int> d_csr_start_, d_csr_col_;
     DevBuf<double> d_csr_d_;
     DevBuf<int> d_adj_start_, d_adj_;
@@ -284,8 +281,8 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
 
     capacity_ = P_.capacity > 0 ? P_.capacity : 1;
     {
-        const char* e = getenv("T2D_STEP");   // dev knob for A/B measurements: "tiled" = k_step_euclid_tiled (measured 3x slower)
-        use_tiled_ = sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID && e && std::string(e) == "tiled";
+        const char* e = getenv("T2D_STEP");   // dev knob for A/B measurements: "legacy" = k_step_euclid_fast + the cs array
+        use_fast2_ = sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID && !(e && std::string(e) == "legacy");
         const char* t = getenv("T2D_COUNT_TIES");
         A_.count_ties = !(t && atoi(t) == 0);
     }
@@ -298,8 +295,8 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     // particle storage
     const size_t C = (size_t)capacity_;
     for (int b = 0; b < 2; ++b) {
-        const bool with_cs = sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID && !use_tiled_;
-        hot_bytes_ = C * (sizeof(Pos3<R>) + (with_cs ? sizeof(double2) : 0) + sizeof(Real2<R>)) + 64;
+        const bool with_cs = sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID && !use_fast2_;
+        hot_bytes_ = C * (sizeof(Pos3<R>) + (with_cs ? sizeof(double2) : 0) + (use_fast2_ ? 2 * sizeof(float4) : 0) + sizeof(Real2<R>)) + 64;
         d_hot_[b].alloc(hot_bytes_);
         d_aux_[b].alloc(C);
         d_rdot_[b].alloc(C);
@@ -314,18 +311,21 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     CK(cudaMemsetAsync(d_counters_.p, 0, sizeof(DevCounters), stream_));
     d_obs_.alloc(T2D_OBS_LEN);
     d_work_.alloc(4);
+    CK(cudaMemsetAsync(d_work_.p, 0, 4 * sizeof(int), stream_));
     d_stage_in_.alloc(C * (16 + 4 + 4 + 24 + 4) + 256);
     d_stage_out_.alloc(C * (16 + 4 + 4 + 24 + 16 + 4 + 4 + 16 + 4) + 256);
 
     auto carve = [&](int b) {
-        const bool with_cs = sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID && !use_tiled_;
+        const bool with_cs = sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID && !use_fast2_;
         unsigned char* q = d_hot_[b].p;
         Pos3<R>* pos = reinterpret_cast<Pos3<R>*>(q);
         q += C * sizeof(Pos3<R>);
         double2* cs = with_cs ? reinterpret_cast<double2*>(q) : nullptr;
         if (with_cs) q += C * sizeof(double2);
+        float4* rec = use_fast2_ ? reinterpret_cast<float4*>(q) : nullptr;
+        if (use_fast2_) q += C * 2 * sizeof(float4);
         Real2<R>* uv = reinterpret_cast<Real2<R>*>(q);
-        return ParticleArrays<R>{pos, uv, d_aux_[b].p, d_rdot_[b].p, d_color_[b].p, cs};
+        return ParticleArrays<R>{pos, uv, d_aux_[b].p, d_rdot_[b].p, d_color_[b].p, cs, rec};
     };
     A_.cur = carve(0);
     A_.alt = carve(1);
@@ -643,92 +643,14 @@ template <typename R> void Engine<R>::build_vox()
     for (int k = 0; k < 3; ++k) A_.vox.origin[k] = (R)org[k];
     A_.vox.inv_cell = (R)(1.0 / cs);
     alloc_buckets((int)base + 1);   // + the overflow bucket
-    if (use_tiled_) build_tiles(words, order, nc, nwx, (int)base);
-}
-
-// Static tiles of the sparse row index (t2d_internal.h DevTiles): for every run of `tile_cells` consecutive compact cells,
-// the merged list of compact-cell intervals that the 3 x 3 rows of 3 x-adjacent cells of its cells cover — exactly the
-// runs row_range() (kernels.cuh) will produce for the tile's particles, computed here from the same words table.
-template <typename R>
-void Engine<R>::build_tiles(const std::vector<uint2>& words, const std::vector<std::pair<uint64_t, size_t>>& order, const int nc[3],
-                            int nwx, int M)
-{
-    // a tile is one warp's unit of work: about one warp-load of particles (32) at the context's capacity
-    int tc = (int)std::max(8.0, std::min(4096.0, 32.0 * (double)std::max(M, 1) / (double)std::max(capacity_, 1)));
-    if (const char* e = getenv("T2D_TILE_CELLS"))
-        if (atoi(e) > 0) tc = atoi(e);
-    int gap = 4;
-    if (const char* e = getenv("T2D_TILE_GAP")) gap = std::max(0, atoi(e));
-    const int ntiles = (M + tc - 1) / tc;
-    // coordinates of every compact cell, in index order (rows in Morton order, x ascending inside a row)
-    std::vector<int> cx((size_t)M), cy((size_t)M), cz((size_t)M);
-    {
-        size_t k = 0;
-        for (auto& o : order) {
-            const int y = (int)(o.second % (size_t)nc[1]), z = (int)(o.second / (size_t)nc[1]);
-            for (int w = 0; w < nwx; ++w) {
-                unsigned bits = words[o.second * nwx + w].x;
-                while (bits) {
-                    const int b = __builtin_ctz(bits);
-                    bits &= bits - 1;
-                    cx[k] = w * 32 + b;
-                    cy[k] = y;
-                    cz[k] = z;
-                    ++k;
-                }
-            }
-        }
-        if (k != (size_t)M) throw CudaError{"internal: cell enumeration does not match the index"};
+    if (use_fast2_) {   // static neighbourhood table of every compact cell (+ the overflow bucket's unused entry)
+        d_nbr_.alloc(((size_t)base + 1) * NBR_STRIDE);
+        Launch<R>::build_nbr(A_.vox, d_nbr_.p, stream_);
+        launches_++;
+        CK(cudaStreamSynchronize(stream_));
+        CK(cudaGetLastError());
+        A_.nbr = d_nbr_.p;
     }
-    auto rank = [&](int x, int y, int z) {   // compact index of the first indexed cell at or after x in row (y, z)
-        const uint2 e = words[((size_t)z * nc[1] + y) * nwx + (x >> 5)];
-        return (int)e.y + __builtin_popcount(e.x & ((1u << (x & 31)) - 1u));
-    };
-    std::vector<int> istart((size_t)ntiles + 1, 0);
-    std::vector<int2> ints;
-    std::vector<std::pair<int, int>> iv;
-    long long unstaged = 0, total_ints = 0;
-    for (int t = 0; t < ntiles; ++t) {
-        iv.clear();
-        const int k0 = t * tc, k1 = std::min(M, k0 + tc);
-        for (int k = k0; k < k1; ++k) {
-            const int x0 = cx[k];
-            if (x0 < 1 || x0 > nc[0] - 2) continue;   // row_range: empty
-            for (int m = 0; m < 9; ++m) {
-                const int y = cy[k] + (m % 3) - 1, z = cz[k] + (m / 3) - 1;
-                if (y < 0 || y >= nc[1] || z < 0 || z >= nc[2]) continue;
-                const int lo = rank(x0 - 1, y, z), hi = rank(x0 + 2, y, z);
-                if (hi > lo && (iv.empty() || iv.back() != std::make_pair(lo, hi))) iv.emplace_back(lo, hi);
-            }
-        }
-        std::sort(iv.begin(), iv.end());
-        size_t first = ints.size();
-        for (auto& p : iv) {
-            if (ints.size() > first && p.first <= ints.back().y + gap) {   // runs a few cells apart travel as one copy
-                if (p.second > ints.back().y) ints.back().y = p.second;
-            } else {
-                ints.push_back(make_int2(p.first, p.second));
-            }
-        }
-        if (ints.size() - first > 32) {   // TILE_IMAX: the tile reads global memory instead (same results)
-            ints.resize(first);
-            unstaged++;
-        }
-        total_ints += (long long)(ints.size() - first);
-        istart[(size_t)t + 1] = (int)ints.size();
-    }
-    if (ints.empty()) ints.push_back(make_int2(0, 0));
-    if (getenv("T2D_VERBOSE"))
-        fprintf(stderr, "t2d: %d cells, %d tiles of %d cells, %.1f intervals per tile, %lld tiles not staged\n", M, ntiles, tc,
-                ntiles ? (double)total_ints / ntiles : 0.0, unstaged);
-    d_tile_istart_.upload(istart, stream_);
-    d_tile_ints_.upload(ints, stream_);
-    CK(cudaStreamSynchronize(stream_));
-    A_.tiles.ntiles = ntiles;
-    A_.tiles.tile_cells = tc;
-    A_.tiles.istart = d_tile_istart_.p;
-    A_.tiles.ints = d_tile_ints_.p;
-    A_.tiles.queue = d_work_.p + 1;
 }
 
 template <typename R> void Engine<R>::apply_params()
@@ -1068,7 +990,9 @@ template <typename R> void Engine<R>::comm_phase1()
     prof_mark();
     if (halo_valid_) {
         A_.step = (uint64_t)step_index;
-        if (!(use_tiled_ && Launch<R>::step_euclid_tiled(A_, sm_count_, stream_)))
+        if (use_fast2_ && Launch<R>::step_fast2(A_, true, sm_count_, stream_))
+            A_.queue_flip ^= 1;
+        else
             Launch<R>::step_euclid(A_, true, stream_);   // cur -> alt; classifies + packs every particle it has just moved
         std::swap(A_.cur, A_.alt);
         launches_++;
@@ -1146,7 +1070,9 @@ template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int
     A_.step = (uint64_t)step_index;
     mark();
     if (P_.neigh_mode == T2D_NEIGH_EUCLID) {
-        if (!(moving && use_tiled_ && Launch<R>::step_euclid_tiled(A_, sm_count_, stream_)))
+        if (use_fast2_ && Launch<R>::step_fast2(A_, moving, sm_count_, stream_))
+            A_.queue_flip ^= 1;
+        else
             Launch<R>::step_euclid(A_, moving, stream_);   // cur -> alt (+ next keys)
         launches_++;
         mark();

@@ -109,55 +109,67 @@ template <typename R> __device__ __forceinline__ int vox_index(const DevVox<R>& 
     return (int)e.y + __popc(e.x & ((1u << bit) - 1u));
 }
 
-// slot range [b, e) of the particles in cells (x0 - 1 .. x0 + 1, y, z).  Compact indices ascend along x inside a
-// row (also across its words), so the particles of the run are contiguous in the sorted state whichever of its
-// cells are occupied.  Every row ends with a spare word whose base is the row's end, so word (x >> 5) exists for
-// x = ncx.  Empty (b == e) outside the grid.
-template <typename R> __device__ __forceinline__ void row_range(const StepArgs<R>& a, int x0, int y, int z, int& b, int& e)
+// compact-cell run [lo, hi) of the cells (x0 - 1 .. x0 + 1, y, z).  Compact indices ascend along x inside a row (also
+// across its words), so the particles of the run are contiguous in the sorted state whichever of its cells are
+// occupied.  Every row ends with a spare word whose base is the row's end, so word (x >> 5) exists for x = ncx.
+// Empty (lo == hi == 0) outside the grid.
+template <typename R> __device__ __forceinline__ void row_cells(const DevVox<R>& vx, int x0, int y, int z, int& lo, int& hi)
 {
-    const DevVox<R>& vx = a.vox;
-    b = e = 0;
+    lo = hi = 0;
     if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz || x0 < 1 || x0 > vx.ncx - 2) return;
     const int xl = x0 - 1, xh = x0 + 2;   // ranks of xl and xh bound the run
     const uint2* row = vx.words + ((size_t)z * vx.ncy + y) * vx.nwx;
     const uint2 e0 = __ldg(row + (xl >> 5));
-    const int lo = (int)e0.y + __popc(e0.x & ((1u << (xl & 31)) - 1u));
-    int hi;
+    const int l = (int)e0.y + __popc(e0.x & ((1u << (xl & 31)) - 1u));
+    int h;
     if ((xh >> 5) == (xl >> 5)) {
-        hi = (int)e0.y + __popc(e0.x & ((1u << (xh & 31)) - 1u));
+        h = (int)e0.y + __popc(e0.x & ((1u << (xh & 31)) - 1u));
     } else {   // the run straddles two words of the row
         const uint2 e1 = __ldg(row + (xh >> 5));
-        hi = (int)e1.y + __popc(e1.x & ((1u << (xh & 31)) - 1u));
+        h = (int)e1.y + __popc(e1.x & ((1u << (xh & 31)) - 1u));
     }
+    if (h > l) {
+        lo = l;
+        hi = h;
+    }
+}
+
+// slot range [b, e) of the particles in those cells
+template <typename R> __device__ __forceinline__ void row_range(const StepArgs<R>& a, int x0, int y, int z, int& b, int& e)
+{
+    int lo, hi;
+    row_cells<R>(a.vox, x0, y, z, lo, hi);
+    b = e = 0;
     if (hi > lo) {
         b = a.start[lo];
         e = a.start[hi];
     }
 }
 
-// the same, also returning the compact index of the run's first cell (the tiled kernel looks its staged copy up by it)
-template <typename R>
-__device__ __forceinline__ void row_range_lo(const StepArgs<R>& a, int x0, int y, int z, int& b, int& e, int& clo)
+// setup: the static neighbourhood table (t2d_internal.h NBR_STRIDE).  One thread per 32-cell word of the row index.
+template <typename R> __global__ void __launch_bounds__(256) k_build_nbr(DevVox<R> vx, int2* nbr)
 {
-    const DevVox<R>& vx = a.vox;
-    b = e = 0;
-    clo = 0;
-    if ((unsigned)y >= (unsigned)vx.ncy || (unsigned)z >= (unsigned)vx.ncz || x0 < 1 || x0 > vx.ncx - 2) return;
-    const int xl = x0 - 1, xh = x0 + 2;
-    const uint2* row = vx.words + ((size_t)z * vx.ncy + y) * vx.nwx;
-    const uint2 e0 = __ldg(row + (xl >> 5));
-    const int lo = (int)e0.y + __popc(e0.x & ((1u << (xl & 31)) - 1u));
-    int hi;
-    if ((xh >> 5) == (xl >> 5)) {
-        hi = (int)e0.y + __popc(e0.x & ((1u << (xh & 31)) - 1u));
-    } else {
-        const uint2 e1 = __ldg(row + (xh >> 5));
-        hi = (int)e1.y + __popc(e1.x & ((1u << (xh & 31)) - 1u));
-    }
-    if (hi > lo) {
-        b = a.start[lo];
-        e = a.start[hi];
-        clo = lo;
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nwords = (size_t)vx.ncz * vx.ncy * vx.nwx;
+    if (w >= nwords) return;
+    const uint2 e = vx.words[w];
+    unsigned bits = e.x;
+    if (!bits) return;
+    const size_t row = w / vx.nwx;
+    const int wx = (int)(w % vx.nwx), y = (int)(row % vx.ncy), z = (int)(row / vx.ncy);
+    int idx = (int)e.y;
+    while (bits) {
+        const int x0 = wx * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        int2* out = nbr + (size_t)idx * NBR_STRIDE;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+            int lo, hi;
+            row_cells<R>(vx, x0, y + (m % 3) - 1, z + (m / 3) - 1, lo, hi);
+            out[m] = make_int2(lo, hi);
+        }
+        out[9] = make_int2(0, 0);
+        ++idx;
     }
 }
 
@@ -278,7 +290,8 @@ template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<
     const int s = a.start[key] + (int)a.rank[i];
     const Pos3<R> P = a.cur.pos[i];
     a.alt.pos[s] = P;
-    a.alt.uv[s] = a.cur.uv[i];
+    const Real2<R> U = a.cur.uv[i];
+    a.alt.uv[s] = U;
     a.alt.aux[s] = a.cur.aux[i];
     a.alt.rdot[s] = a.cur.rdot[i];
     a.alt.color[s] = a.cur.color[i];
@@ -287,6 +300,12 @@ template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<
         unsigned long long fb = 0;
         a.alt.cs[s] = trig_lookup(a.trig_d, (int)P.w, fb);
         if (fb) atomicAdd(&a.counters->trig_fallbacks, fb);
+    }
+    if (a.alt.rec) {   // fp32 fast path: the 32-byte record the neighbour pass of the next step reads (t2d_internal.h)
+        const int n = (int)P.w;
+        const int slot = (unsigned)n <= 360u ? n : 361;   // index into the shared-memory trig table of k_step_fast2, 361 = not in it
+        a.alt.rec[2 * (size_t)s] = make_float4((float)P.x, (float)P.y, (float)P.z, __int_as_float(slot));
+        a.alt.rec[2 * (size_t)s + 1] = make_float4((float)U.x, (float)U.y, __int_as_float((int)key), __int_as_float(n));
     }
 }
 
@@ -754,12 +773,10 @@ struct PairAcc {
 // (ForceHelper.cpp:84-104).  d = 0 -> d := 0.001 (ForceHelper.cpp:59-62): the particle itself (ui - uj = 0, no force)
 // or one whose 3-D position coincides with it in fp32 while its uv does not — common inside the dense clumps the
 // lift produces, so the rule matters: without it 1/d is unbounded and a single pair throws both particles off the chart.
-__device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const double2* __restrict__ trig,
-                                          const Real2<float>* __restrict__ uv, int j, float heading_j, float d2,
-                                          const Real2<float>& ui, float g1, float g0, PairAcc& acc, unsigned long long& trig_fb)
+__device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const Real2<float>* __restrict__ uv, int j, float d2,
+                                          const Real2<float>& ui, float g1, float g0, PairAcc& acc)
 {
-    // (cos, sin) of the neighbour's heading: the per-particle array the sort makes (legacy layout), else the host-libm table
-    const double2 t = cs ? cs[j] : trig_lookup(trig, (int)heading_j, trig_fb);
+    const double2 t = cs[j];
     const Real2<float> uj = uv[j];
     acc.mx += t.x;
     acc.my += t.y;
@@ -769,7 +786,7 @@ __device__ __forceinline__ void pair_term(const double2* __restrict__ cs, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// per-particle tail of the fp32 fast path, shared by k_step_euclid_fast and k_step_euclid_tiled: speed and velocity
+// per-particle tail of the fp32 fast path, shared by k_step_fast2 (step_fast2.cuh) and the legacy k_step_euclid_fast: speed and velocity
 // (Locomotion.cpp:71-81), heading after alignment (+ noise), Euler step (Locomotion.cpp:84), seam re-entry, validation,
 // UV point location (previous-face hint, else first containing face of the grid cell, else the distance arg-min),
 // lift, next bucket key / slab classification.  `own` = (cos, sin) of the particle's OLD heading.
@@ -1004,12 +1021,12 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
                 asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tadd.u32 t, %1, -1;\n\tsetp.lt.u32 p, t, %2;\n\t@p add.s32 %0, %0, 1;\n\t}"
                     : "+r"(color)
                     : "r"(__float_as_uint(d2)), "r"(r2c_bits));
-                if (count_ties) {   // near-cutoff candidates: the "logged ties" of the parity bar (see step_tiled.cuh cand_loop)
+                if (count_ties) {   // near-cutoff candidates: the "logged ties" of the parity bar (see step_fast2.cuh)
                     const unsigned bm1 = __float_as_uint(d2) - 1u;
                     if ((bm1 - tie_s_lo) <= 16u || (bm1 - tie_c_lo) <= 16u) ncut++;
                 }
                 if (d2 < r2s) {
-                    pair_term(cs, a.trig_d, uv, jb + t, Pj.w, d2, ui, g1, g0, acc, trig_fb);
+                    pair_term(cs, uv, jb + t, d2, ui, g1, g0, acc);
                     hits++;
                 }
             }
@@ -1018,7 +1035,7 @@ template <bool MOVING> __global__ void __launch_bounds__(STEP_THREADS, T2D_FAST_
 
     __syncwarp();   // reconverge: lanes leave the candidate loops at different times, the tail below is the same for all
     if (live) {
-        const double2 own = cs ? cs[i] : trig_lookup(a.trig_d, (int)a.cur.pos[i].w, trig_fb);
+        const double2 own = cs[i];
         fast_epilogue<MOVING>(a, i, ai, ui, own, acc, color, hits, npairs, nties);
     }
     // diagnostic counters: one atomic per warp

@@ -1,6 +1,6 @@
 // step_f32.cu — the fp32 fast path (FMA contraction allowed).
 #include "kernels.cuh"
-#include "step_tiled.cuh"
+#include "step_fast2.cuh"
 namespace t2d {
 template struct Launch<float>;
 }

@@ -1,0 +1,392 @@
+// step_fast2.cuh — k_step_fast2: stages 2-5 of the step for the Euclidean criterion, fp32 fast path (the benchmarked kernel).
+//
+// Replaces (reference, /root/reference/src/simulation): Locomotion::get_dist_vect + get_distances_between_particles
+// (Locomotion.cpp:94-162), ForceHelper::calculate_forces_between_particles (Locomotion/ForceHelper.cpp:34-104),
+// OrientationHelper::calculate_average_n_within_distance (Locomotion/OrientationHelper.cpp:29-116), the Euler step
+// (Locomotion.cpp:71-84), EuclideanTiling (Locomotion/EuclideanTiling.cpp:31-208), CellHelper::get_r3d (CellHelper.cpp:71-229),
+// Validation (Validation.cpp:40-72) and count_particle_neighbors (2DTissue.cpp:254-268).
+//
+// Same arithmetic as the round-1 kernel (k_step_euclid_fast, kept behind T2D_STEP=legacy); what changed is where the
+// instructions and the waiting went (ncu, profiles/r01_step_fast_lines.md: 17 % of the kernel's instructions found the nine
+// candidate ranges, 18 % of its stall samples waited for the cs[j] gather, issue slots 53 % busy):
+//   * ONE 32-byte record per candidate {x, y, z, heading | u, v, cell, -} (made by the counting-sort scatter): the distance
+//     test reads the first half, an in-range pair the second half of the SAME sector — no second and third gather;
+//   * (cos n, sin n) of a neighbour's heading comes from a 361-entry copy of the host-libm table in shared memory, loaded
+//     once per CTA by the TMA unit (cp.async.bulk + mbarrier); the 16-byte-per-particle cs array no longer exists;
+//   * the nine candidate ranges of a particle are two loads each from the STATIC neighbourhood table of its cell
+//     (t2d_internal.h NBR_STRIDE) instead of a word lookup, two popcounts and bounds logic per row; the ranges are ordered
+//     longest-first by a sorting network on packed 32-bit keys (2 instructions per compare-exchange);
+//   * persistent CTAs, warps independent of each other (no CTA barrier after the table load): every warp pulls runs of
+//     consecutive 32-slot chunks from a device-side queue.
+#pragma once
+#include "kernels.cuh"
+
+namespace t2d {
+
+constexpr int F2_THREADS = 128;
+#ifndef T2D_F2_MIN_BLOCKS
+#define T2D_F2_MIN_BLOCKS 8
+#endif
+#ifndef T2D_F2_GRAB
+#define T2D_F2_GRAB 2   // consecutive 32-slot chunks per queue grab (the second chunk finds most of its candidates in L1)
+#endif
+#ifndef T2D_F2_UNROLL
+#define T2D_F2_UNROLL 4
+#endif
+constexpr int F2_TRIG_N = 361;   // headings 0..360: what alignment produces (OrientationHelper.cpp:102-116); seam re-entry makes the rest
+constexpr unsigned F2_TIE_ULPS = 8;
+
+struct alignas(128) F2Smem {
+    double2 trig[F2_TRIG_N + 3];            // entries 361 and 362 are overwritten with (0, 0): see f2_candidate
+    int rkey[NRANGE][F2_THREADS];           // per thread (column): ranges longest first, (length << 4) | row
+    int rbeg[NRANGE][F2_THREADS];           // per thread: first slot of row m's range (not sorted)
+    unsigned long long bar;
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) --------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
+{
+    while (!mbar_try_wait(b, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared; dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+
+struct F2Consts {
+    float r2s, r2c, g1, g0;
+    unsigned tie_s_lo, tie_c_lo;   // bits(r^2) - F2_TIE_ULPS - 1
+};
+struct F2Acc {
+    float fx = 0.0f, fy = 0.0f;
+    double mx = 0.0, my = 0.0;
+    int color = 0, hits = 0;
+    unsigned ties = 0;
+};
+
+// one 32-byte record with ONE load instruction (LDG.E.256, new on sm_100): {x, y, z, trig slot | u, v, cell, heading}
+struct F2Rec { float x, y, z; unsigned slot; float u, v; int cell, heading; };
+__device__ __forceinline__ F2Rec f2_load(const float4* __restrict__ q)
+{
+    F2Rec r;
+    asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=r"(r.slot), "=f"(r.u), "=f"(r.v), "=r"(r.cell), "=r"(r.heading)
+        : "l"(q));
+    return r;
+}
+__device__ __forceinline__ double2 f2_lds_trig(uint32_t addr)
+{
+    double2 t;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(addr));
+    return t;
+}
+
+// One candidate, branch-free.  d^2 in fp32; colour count (0 != d <= 2.4 sigma, 2DTissue.cpp:254-268); in-range pair:
+// F_ij / d = -k / d + k / 2 sigma (ForceHelper.cpp:84-104) as one FMA on 1/d, d = 0 -> 0.001 (ForceHelper.cpp:59-62); the unit
+// vector of the neighbour's heading from the shared-memory copy of the host-libm table, summed in double
+// (OrientationHelper.cpp:43-58).  About 56 % of the candidates are in range, so some lane of the warp needs the pair term
+// almost every time: it is computed for every candidate and masked — an out-of-range candidate reads the table's zero
+// entry (slot 362) and gets g = 0.  A heading outside the table has slot 361 (also zero); `oob` then sends the thread through
+// the rare global-table path after the group.  TIES: log candidates within F2_TIE_ULPS ulps of a squared cutoff — a
+// neighbour-set or colour difference against the fp64 oracle must be one of these (tests/test_gpu_fastpath.py).
+template <bool TIES>
+__device__ __forceinline__ void f2_candidate(const F2Rec& J, const float px, const float py, const float pz, const float2 ui,
+                                             const F2Consts& k, const uint32_t s_trig, F2Acc& acc, bool& oob)
+{
+    const float dx = px - J.x, dy = py - J.y, dz = pz - J.z;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    const bool p = d2 < k.r2s, z = d2 == 0.0f;
+    acc.color += (d2 <= k.r2c && !z) ? 1 : 0;
+    if (TIES) {
+        const unsigned bm1 = __float_as_uint(d2) - 1u;
+        if ((bm1 - k.tie_s_lo) <= 2u * F2_TIE_ULPS || (bm1 - k.tie_c_lo) <= 2u * F2_TIE_ULPS) acc.ties++;
+    }
+    const unsigned idx = p ? J.slot : (unsigned)(F2_TRIG_N + 1);
+    const double2 tr = f2_lds_trig(s_trig + idx * 16u);
+    acc.mx += tr.x;
+    acc.my += tr.y;
+    float inv = rsqrtf(d2);
+    inv = z ? 1000.0f : inv;
+    float g = fmaf(inv, k.g1, k.g0);
+    g = p ? g : 0.0f;
+    acc.fx = fmaf(g, ui.x - J.u, acc.fx);
+    acc.fy = fmaf(g, ui.y - J.v, acc.fy);
+    acc.hits += p ? 1 : 0;
+    oob = oob || idx == (unsigned)F2_TRIG_N;
+}
+// the rare path: an in-range neighbour whose heading is outside 0..360 (it crossed the seam in the last step)
+template <int = 0>
+__device__ __noinline__ double2 f2_oob_term(const double2* g_trig, float r2s, float px, float py, float pz, float jx, float jy, float jz,
+                                            unsigned slot, int heading)
+{
+    const float dx = px - jx, dy = py - jy, dz = pz - jz;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    if (!(d2 < r2s) || slot != (unsigned)F2_TRIG_N) return make_double2(0.0, 0.0);
+    unsigned long long fb = 0;
+    return trig_lookup(g_trig, heading, fb);
+}
+
+// a particle outside the static index (overflow bucket; cannot happen for points on the mesh): its ranges from its coordinates,
+// straight into the thread's shared-memory columns (arguments by value: a reference to the kernel's parameter block would
+// force a copy of it into local memory)
+static __device__ __noinline__ void f2_ranges_by_coords(DevVox<float> vx, const int* start, float x, float y, float z, int* rbeg,
+                                                        int* rkey)
+{
+    Pos3<float> P = {x, y, z, 0.0f};
+    int c[3];
+    cell_coords<float>(vx, P, c);
+    for (int m = 0; m < 9; ++m) {
+        int lo, hi, b = 0, len = 0;
+        row_cells<float>(vx, c[0], c[1] + (m % 3) - 1, c[2] + (m / 3) - 1, lo, hi);
+        if (hi > lo) {
+            b = start[lo];
+            len = start[hi] - b;
+        }
+        rbeg[m * F2_THREADS] = b;
+        rkey[m * F2_THREADS] = (min(len, 0x07ffffff) << 4) | m;
+    }
+}
+
+template <bool MOVING, bool TIES>
+__global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(StepArgs<float> a, int* queue, int* queue_next)
+{
+    typedef float R;
+    __shared__ F2Smem sm;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x == 0) *queue_next = 0;   // the queue of the NEXT launch (launches alternate between two counters)
+    }
+    __syncthreads();
+    if (tid == 0) {    // cos/sin of 0..360 degrees as the host's libm gives them: one bulk copy per CTA
+        constexpr unsigned bytes = (unsigned)(sizeof(double2) * (F2_TRIG_N + 3));
+        mbar_arrive_expect_tx(&sm.bar, bytes);
+        bulk_g2s(sm.trig, a.trig_d + (0 - TRIG_MIN), bytes, &sm.bar);
+    }
+
+    F2Consts k;
+    {
+        k.r2s = a.two_sigma * a.two_sigma;
+        k.r2c = a.color_r * a.color_r;
+        k.g1 = -a.k;
+        k.g0 = a.k / a.two_sigma;
+        k.tie_s_lo = __float_as_uint(k.r2s) - F2_TIE_ULPS - 1u;
+        k.tie_c_lo = __float_as_uint(k.r2c) - F2_TIE_ULPS - 1u;
+    }
+    const int nres = resident_count<R>(a);
+    const int ngrabs = (nres + 32 * T2D_F2_GRAB - 1) / (32 * T2D_F2_GRAB);
+    const int M = a.vox.M;
+    const float4* __restrict__ rec = a.cur.rec;
+    const int* __restrict__ start = a.start;
+    const int ob = start[M], ol = start[M + 1] - ob;   // overflow bucket: normally empty
+    unsigned npairs_w = 0, nties_w = 0, ncut_w = 0, fb_w = 0;
+
+    int next = 0;
+    if (lane == 0) next = atomicAdd(queue, 1);
+    mbar_wait(&sm.bar, 0);   // the table has landed (every thread observes the barrier itself)
+    if (tid < 2) sm.trig[F2_TRIG_N + tid] = make_double2(0.0, 0.0);
+    __syncthreads();
+    const uint32_t s_trig = smem_u32(sm.trig);
+
+    for (;;) {
+        const int grab = __shfl_sync(0xffffffffu, next, 0);
+        if (grab >= ngrabs) break;
+        if (lane == 0) next = atomicAdd(queue, 1);   // in flight while this grab is processed
+#pragma unroll 1
+        for (int sub = 0; sub < T2D_F2_GRAB; ++sub) {
+            const int i = (grab * T2D_F2_GRAB + sub) * 32 + lane;
+            const bool resident = i < nres;
+            const int4 ai = resident ? a.cur.aux[i] : make_int4(0, 0, 0, ORIGIN_DEAD);
+            const bool live = resident && ai.w >= 0;   // slab mode: halo copies are read by others, never advanced
+            if (MOVING && resident && !live) {
+                a.alt.aux[i] = make_int4(0, -1, ai.z, ORIGIN_DEAD);
+                a.key[i] = KEY_DROP;
+            }
+            F2Acc acc;
+            float2 ui = make_float2(0.0f, 0.0f);
+            int nh = 0;
+            if (live) {
+                const F2Rec self = f2_load(rec + 2 * (size_t)i);
+                const float px = self.x, py = self.y, pz = self.z;
+                nh = self.heading;
+                ui = make_float2(self.u, self.v);
+                const int cell = self.cell;
+                int key[9];
+                if (cell < M) {
+                    const int4* nb = reinterpret_cast<const int4*>(a.nbr + (size_t)cell * NBR_STRIDE);
+                    int4 q[5];
+#pragma unroll
+                    for (int h = 0; h < 5; ++h) q[h] = __ldg(nb + h);
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) {
+                        const int lo = (m & 1) ? q[m >> 1].z : q[m >> 1].x, hi = (m & 1) ? q[m >> 1].w : q[m >> 1].y;
+                        int b = 0, len = 0;
+                        if (hi > lo) {
+                            b = start[lo];
+                            len = start[hi] - b;
+                        }
+                        sm.rbeg[m][tid] = b;
+                        key[m] = (min(len, 0x07ffffff) << 4) | m;
+                    }
+                } else {
+                    f2_ranges_by_coords(a.vox, start, px, py, pz, &sm.rbeg[0][tid], &sm.rkey[0][tid]);
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) key[m] = sm.rkey[m][tid];
+                }
+                // 9-input sorting network (25 compare-exchanges), longest range first: the lanes of a warp then finish their
+                // m-th range at about the same time (measured in round 1: 67 instead of 92 warp iterations per particle row)
+#define T2D_CSWAP(x, y)                          \
+    {                                            \
+        const int hi_ = max(key[x], key[y]);     \
+        key[y] = min(key[x], key[y]);            \
+        key[x] = hi_;                            \
+    }
+                T2D_CSWAP(0, 1) T2D_CSWAP(3, 4) T2D_CSWAP(6, 7) T2D_CSWAP(1, 2) T2D_CSWAP(4, 5) T2D_CSWAP(7, 8)
+                T2D_CSWAP(0, 1) T2D_CSWAP(3, 4) T2D_CSWAP(6, 7) T2D_CSWAP(0, 3) T2D_CSWAP(3, 6) T2D_CSWAP(0, 3)
+                T2D_CSWAP(1, 4) T2D_CSWAP(4, 7) T2D_CSWAP(1, 4) T2D_CSWAP(2, 5) T2D_CSWAP(5, 8) T2D_CSWAP(2, 5)
+                T2D_CSWAP(1, 3) T2D_CSWAP(5, 7) T2D_CSWAP(2, 6) T2D_CSWAP(4, 6) T2D_CSWAP(2, 4) T2D_CSWAP(2, 3)
+                T2D_CSWAP(5, 6)
+#undef T2D_CSWAP
+                int nr = 0;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) {
+                    sm.rkey[m][tid] = key[m];
+                    nr += key[m] >= 16 ? 1 : 0;
+                }
+                if (ol > 0) {   // the overflow bucket is everybody's candidate
+                    sm.rbeg[9][tid] = ob;
+                    sm.rkey[nr][tid] = (min(ol, 0x07ffffff) << 4) | 9;
+                    nr++;
+                }
+#pragma unroll 1
+                for (int m = 0; m < nr; ++m) {
+                    const int kk = sm.rkey[m][tid];
+                    const int len = kk >> 4, jb = sm.rbeg[kk & 15][tid];
+                    const float4* q = rec + 2 * (size_t)jb;
+                    int t = 0;
+#if T2D_F2_UNROLL > 1
+                    for (; t + T2D_F2_UNROLL <= len; t += T2D_F2_UNROLL, q += 2 * T2D_F2_UNROLL) {
+                        F2Rec J[T2D_F2_UNROLL];
+#pragma unroll
+                        for (int u = 0; u < T2D_F2_UNROLL; ++u) J[u] = f2_load(q + 2 * u);
+                        bool oob = false;
+#pragma unroll
+                        for (int u = 0; u < T2D_F2_UNROLL; ++u) f2_candidate<TIES>(J[u], px, py, pz, ui, k, s_trig, acc, oob);
+                        if (__builtin_expect(oob, 0)) {
+#pragma unroll 1
+                            for (int u = 0; u < T2D_F2_UNROLL; ++u) {
+                                const F2Rec O = f2_load(q + 2 * u);
+                                const double2 tr = f2_oob_term(a.trig_d, k.r2s, px, py, pz, O.x, O.y, O.z, O.slot, O.heading);
+                                acc.mx += tr.x;
+                                acc.my += tr.y;
+                            }
+                        }
+                    }
+#endif
+#pragma unroll 1
+                    for (; t < len; ++t, q += 2) {
+                        const F2Rec J = f2_load(q);
+                        bool oob = false;
+                        f2_candidate<TIES>(J, px, py, pz, ui, k, s_trig, acc, oob);
+                        if (__builtin_expect(oob, 0)) {
+                            const double2 tr = f2_oob_term(a.trig_d, k.r2s, px, py, pz, J.x, J.y, J.z, J.slot, J.heading);
+                            acc.mx += tr.x;
+                            acc.my += tr.y;
+                        }
+                    }
+                }
+            }
+            __syncwarp();   // reconverge: lanes leave the candidate loops at different times, the tail is the same for all
+            unsigned npairs = 0, nties = 0;
+            if (live) {
+                double2 own;
+                if ((unsigned)nh < (unsigned)F2_TRIG_N) {
+                    own = sm.trig[nh];
+                } else {
+                    unsigned long long fb = 0;
+                    own = trig_lookup(a.trig_d, nh, fb);
+                    fb_w += (unsigned)fb;
+                }
+                PairAcc pa;
+                pa.fx = acc.fx;
+                pa.fy = acc.fy;
+                pa.mx = acc.mx;
+                pa.my = acc.my;
+                Real2<R> uir = {ui.x, ui.y};
+                fast_epilogue<MOVING>(a, i, ai, uir, own, pa, acc.color, acc.hits, npairs, nties);
+            }
+            npairs_w += npairs;
+            nties_w += nties;
+            ncut_w += acc.ties;
+        }
+    }
+    // diagnostic counters: one atomic per warp and counter
+    npairs_w = __reduce_add_sync(0xffffffffu, npairs_w);
+    nties_w = __reduce_add_sync(0xffffffffu, nties_w);
+    ncut_w = __reduce_add_sync(0xffffffffu, ncut_w);
+    fb_w = __reduce_add_sync(0xffffffffu, fb_w);
+    if (lane == 0) {
+        if (npairs_w) atomicAdd(&a.counters->pairs_in_range, (unsigned long long)npairs_w);
+        if (nties_w) atomicAdd(&a.counters->ties_trunc, (unsigned long long)nties_w);
+        if (ncut_w) atomicAdd(&a.counters->ties_cutoff, (unsigned long long)ncut_w);
+        if (fb_w) atomicAdd(&a.counters->trig_fallbacks, (unsigned long long)fb_w);
+    }
+}
+
+template <typename R> bool Launch<R>::step_fast2(const StepArgs<R>& a, bool moving, int sm_count, cudaStream_t s)
+{
+    if constexpr (sizeof(R) == 4) {
+        if (!a.cur.rec || !a.nbr) return false;
+        const int n = a.comm.on ? a.comm.capacity : a.N;
+        if (n <= 0) return true;
+        const int ngrabs = div_up(n, 32 * T2D_F2_GRAB);
+        int grid = sm_count * T2D_F2_MIN_BLOCKS;
+        if (grid > div_up(ngrabs, F2_THREADS / 32)) grid = div_up(ngrabs, F2_THREADS / 32);
+        int* q0 = a.work_counter + 1 + (a.queue_flip & 1);   // two queue counters, used alternately: every launch zeroes the
+        int* q1 = a.work_counter + 1 + ((a.queue_flip + 1) & 1);   // other one (the caller flips queue_flip after each launch)
+        if (moving) {
+            if (a.count_ties)
+                k_step_fast2<true, true><<<grid, F2_THREADS, 0, s>>>(a, q0, q1);
+            else
+                k_step_fast2<true, false><<<grid, F2_THREADS, 0, s>>>(a, q0, q1);
+        } else {
+            k_step_fast2<false, true><<<grid, F2_THREADS, 0, s>>>(a, q0, q1);
+        }
+        return true;
+    } else {
+        return false;
+    }
+}
+
+template <typename R> void Launch<R>::build_nbr(const DevVox<R>& vx, int2* nbr, cudaStream_t s)
+{
+    const size_t nwords = (size_t)vx.ncz * vx.ncy * vx.nwx;
+    if (nwords) k_build_nbr<R><<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(vx, nbr);
+}
+
+}  // namespace t2d

@@ -54,19 +54,11 @@ template <typename R> struct DevVox {
     R inv_cell = 0;
 };
 
-// Static tiling of the sparse row index for the staged fast path (k_step_euclid_tiled).  The set of surface cells never
-// changes, so which cells a cell's 3 x 3 x 3 neighbourhood touches is known when the index is built: compact cells are cut
-// into tiles of `tile_cells` consecutive indices (= consecutive slots of the sorted state), and for every tile the host
-// merges the compact-index runs its cells can see into at most TILE_IMAX intervals [lo, hi).  At run time an interval is
-// the slot range [start[lo], start[hi]) — one contiguous piece of pos[] / uv[] — which a CTA stages into shared memory
-// with cp.async.bulk before its threads walk their candidate ranges there.
-struct DevTiles {
-    int ntiles = 0;                // tiles over compact cells [0, M); tile number `ntiles` is the overflow bucket
-    int tile_cells = 0;
-    const int* istart = nullptr;   // [ntiles + 1] CSR into ints; an empty list = tile not staged (too many intervals)
-    const int2* ints = nullptr;    // merged intervals, ascending lo
-    int* queue = nullptr;          // dynamic tile counter, zeroed before every launch
-};
+// Static neighbourhood table of the sparse row index (fp32 fast path, k_step_fast2).  The set of surface cells never
+// changes, so WHICH compact cells the 3 x 3 rows of 3 x-adjacent cells around a cell cover is known when the index is
+// built: nbr[c * NBR_STRIDE + m] = [lo, hi) in compact-cell numbers for row m = (dy + 1) + 3 (dz + 1), (0, 0) if empty.
+// At run time the candidates are the slots [start[lo], start[hi]): two loads per row instead of a word lookup + popcounts.
+constexpr int NBR_STRIDE = 10;   // 9 rows + one spare entry: 80 bytes per cell, 16-byte aligned
 
 // ---- particle state, SoA, in "slot" order (sorted by bucket key) --------------------------------------
 template <typename R> struct alignas(2 * sizeof(R)) Real2 { R x, y; };
@@ -76,7 +68,9 @@ template <typename R> struct ParticleArrays {
     int4* aux = nullptr;      // x = nearest-vertex id (vertices_3D_active), y = face, z = global id, w = index in the caller's arrays
     Real2<R>* rdot = nullptr; // velocity of the last step (r_dot)
     int* color = nullptr;     // neighbour count of the last step (particles_color)
-    double2* cs = nullptr;    // fp32 Euclid path only: (cos, sin) of the heading as the reference's libm gives them; made by k_scatter
+    double2* cs = nullptr;    // legacy fp32 Euclid kernel only: (cos, sin) of the heading as the reference's libm gives them; made by k_scatter
+    float4* rec = nullptr;    // fp32 Euclid fast path: ONE 32-byte record per slot, made by k_scatter: {x, y, z, trig-table slot},
+                              // {u, v, compact cell, heading} — everything the neighbour pass reads of a candidate, in one sector
 };
 
 // ---- multi-GPU slabs: message records and the device-side description of one rank's slab ----
@@ -147,7 +141,7 @@ template <typename R> struct StepArgs {
     DevMesh<R> mesh;
     DevCSR csr;
     DevVox<R> vox;
-    DevTiles tiles;
+    const int2* nbr = nullptr;     // [(M + 1) * NBR_STRIDE] static neighbourhood table (see NBR_STRIDE)
     DevComm<R> comm;
     // parameters
     R v0, k, two_sigma, color_r, step_size;
@@ -157,7 +151,8 @@ template <typename R> struct StepArgs {
     int mode;
     int write_F;
     int count_ties = 1;            // fp32 fast path: log candidates within 8 ulps of a cutoff in ties_cutoff
-    int* work_counter = nullptr;   // dynamic bucket queue for the table-mode kernel
+    int* work_counter = nullptr;   // [4] dynamic queues: [0] buckets of the table-mode kernel, [1], [2] chunk queues of k_step_fast2
+    int queue_flip = 0;            // which of the two chunk queues the next k_step_fast2 launch uses (it zeroes the other one)
 };
 
 // kernel launchers implemented once per precision (step_f64.cu with --fmad=false, step_f32.cu with FMA)
@@ -167,7 +162,8 @@ template <typename R> struct Launch {
     static void bin(const StepArgs<R>& a, cudaStream_t s);                      // key + rank + histogram of `cur`
     static void scatter(const StepArgs<R>& a, cudaStream_t s);                  // cur -> alt in bucket order
     static void step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s); // stages 2-5 fused, cur -> alt (+ next keys)
-    static bool step_euclid_tiled(const StepArgs<R>& a, int sm_count, cudaStream_t s);   // fp32 only: staged tiles; false = not available
+    static bool step_fast2(const StepArgs<R>& a, bool moving, int sm_count, cudaStream_t s);   // fp32 only (step_fast2.cuh); false = not available
+    static void build_nbr(const DevVox<R>& vx, int2* nbr, cudaStream_t s);      // setup: static neighbourhood table
     static void neigh_table(const StepArgs<R>& a, cudaStream_t s, int sm_count);
     static void wrap_project(const StepArgs<R>& a, cudaStream_t s);             // table mode stages 4b-5, in place (+ next keys)
     static void project_only(const StepArgs<R>& a, cudaStream_t s);             // initial projection (get_r3d)
