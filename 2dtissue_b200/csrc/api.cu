@@ -216,6 +216,15 @@ template <typename R> class Engine : public EngineBase {
     DevBuf<CrEntry> d_cr_;
     DevBuf<uint2> d_vox_words_;
     DevBuf<int2> d_nbr_;
+    DevBuf<float4> d_rec_sentinel_;
+    DevBuf<int> d_src_;                          // lean pipeline: sorted slot -> pre-sort index
+    DevBuf<unsigned long long> d_scan_status_;   // one-pass scan: tile status words
+    unsigned scan_seq_ = 0;                      // launch number of the one-pass scan (tags the status words)
+    int scan_ticket_base_ = 0;                   // value of the scan's ticket counter (d_work_[3]) before the next launch
+    bool lean_ = false;                          // cur holds only rec + aux (+ src): pos / uv / r_dot / colour are stale until materialize()
+    bool lean_ok_ = false;                       // the lean pipeline may be used (fp32 Euclid fast path; T2D_LEAN=0 switches it off)
+    void scan_buckets();
+    void materialize();
     bool use_fast2_ = false;       // fp32 Euclid: k_step_fast2 (step_fast2.cuh) on 32-byte records; T2D_STEP=legacy switches it off
     DevBuf<int> d_csr_start_, d_csr_col_;
     DevBuf<double> d_csr_d_;
@@ -312,6 +321,20 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     d_obs_.alloc(T2D_OBS_LEN);
     d_work_.alloc(4);
     CK(cudaMemsetAsync(d_work_.p, 0, 4 * sizeof(int), stream_));
+    if (use_fast2_) {   // {x, y, z, trig slot 361 = zero entry | u, v, cell, heading}: d^2 overflows to +inf against any real particle
+        int slot = 361;
+        float sl;
+        memcpy(&sl, &slot, 4);
+        const float4 h[2] = {make_float4(1e30f, 1e30f, 1e30f, sl), make_float4(0.f, 0.f, 0.f, 0.f)};
+        d_rec_sentinel_.alloc(2);
+        CK(cudaMemcpyAsync(d_rec_sentinel_.p, h, sizeof(h), cudaMemcpyHostToDevice, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        A_.rec_sentinel = d_rec_sentinel_.p;
+        d_src_.alloc(C);
+        A_.src = d_src_.p;
+        const char* le = getenv("T2D_LEAN");
+        lean_ok_ = !(le && atoi(le) == 0);
+    }
     d_stage_in_.alloc(C * (16 + 4 + 4 + 24 + 4) + 256);
     d_stage_out_.alloc(C * (16 + 4 + 4 + 24 + 16 + 4 + 4 + 16 + 4) + 256);
 
@@ -536,6 +559,30 @@ template <typename R> void Engine<R>::alloc_buckets(int nbuckets)
     A_.count = d_count_.p;
     A_.start = d_start_.p;
     A_.blocksums = d_blocksums_.p;
+    d_scan_status_.alloc((size_t)scan_blocks(nbuckets) + 8);
+    CK(cudaMemsetAsync(d_scan_status_.p, 0, ((size_t)scan_blocks(nbuckets) + 8) * sizeof(unsigned long long), stream_));
+}
+
+// exclusive scan of the bucket histogram into A_.start (zeroes the histogram): one launch
+template <typename R> void Engine<R>::scan_buckets()
+{
+    const int nb = scan_blocks(A_.M);
+    if (scan_ticket_base_ > (1 << 30)) {   // keep the ticket counter far from overflow
+        CK(cudaMemsetAsync(d_work_.p + 3, 0, sizeof(int), stream_));
+        scan_ticket_base_ = 0;
+    }
+    launch_scan_onepass(A_.count, A_.start, d_scan_status_.p, d_work_.p + 3, scan_ticket_base_, ++scan_seq_, A_.M, stream_);
+    scan_ticket_base_ += nb;
+    launches_++;
+}
+
+// lean pipeline -> full sorted state (pos, uv, r_dot, colour), for everything that is not k_step_fast2
+template <typename R> void Engine<R>::materialize()
+{
+    if (!lean_) return;
+    Launch<R>::expand(A_, stream_);
+    launches_++;
+    lean_ = false;
 }
 
 // Sparse row index of the 3-D cell list (t2d_internal.h DevVox).  Cell edge = rmax*(1+margin); the cells a
@@ -689,6 +736,8 @@ template <typename R> int Engine<R>::set_params(const t2d_params* p)
     if (comm_on_ && (p->sigma != P_.sigma || p->color_factor != P_.color_factor))
         throw CudaError{"sigma / color_factor cannot change while the slab exchange is active: t2d_comm_destroy, "
                         "t2d_set_params, then t2d_comm_init again"};
+    CK(cudaSetDevice(device_));
+    materialize();
     int cap = P_.capacity;
     P_ = *p;
     P_.capacity = cap;
@@ -747,12 +796,13 @@ template <typename R> void Engine<R>::resort(bool keys_ready)
         Launch<R>::bin(A_, stream_);
         launches_++;
     }
-    launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
+    scan_buckets();
     l2_window(A_.alt.pos);
     Launch<R>::scatter(A_, stream_);
     std::swap(A_.cur, A_.alt);
-    launches_ += 4;
+    launches_ += 1;
     sorted_ = true;
+    lean_ = false;
 }
 
 template <typename R>
@@ -765,6 +815,7 @@ int Engine<R>::set_state(int N, const double* uv, const int* heading, const int*
         for (int i = 0; i < N; ++i)
             if (vid[i] < 0 || vid[i] >= chart_.V) throw CudaError{"vid out of range"};
     CK(cudaSetDevice(device_));
+    lean_ = false;   // everything resident is replaced
     this->N = N;
     A_.N = N;
     if (comm_on_) {   // project_only / ingest run on the host-known count; the slab count is installed afterwards
@@ -819,6 +870,7 @@ template <typename R> int Engine<R>::owned_count()
 template <typename R> int Engine<R>::download(double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, int* face)
 {
     CK(cudaSetDevice(device_));
+    materialize();
     int resident = this->N;
     const int* offsets = nullptr;
     if (comm_on_) {
@@ -858,6 +910,7 @@ template <typename R> int Engine<R>::download(double* uv, int* heading, int* vid
 template <typename R> int Engine<R>::download_ids(uint32_t* ids)
 {
     CK(cudaSetDevice(device_));
+    materialize();
     int resident = this->N;
     const int* offsets = nullptr;
     if (comm_on_) {
@@ -880,6 +933,7 @@ template <typename R>
 int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* cuts, EngineBase* const* group)
 {
     CK(cudaSetDevice(device_));
+    materialize();
     if (P_.neigh_mode != T2D_NEIGH_EUCLID) throw CudaError{"slab mode supports the Euclidean criterion only"};
     if (world < 1 || rank < 0 || rank >= world) throw CudaError{"bad rank / world"};
     if (world > T2D_MAX_WORLD) throw CudaError{"at most 16 slabs"};
@@ -1037,12 +1091,12 @@ template <typename R> void Engine<R>::comm_phase2()
     Launch<R>::comm_unpack_far(A_, stream_);
     if (A_.comm.world > 1) launches_++;
     prof_mark();
-    launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
+    scan_buckets();
     prof_mark();
     l2_window(A_.alt.pos);
     Launch<R>::scatter(A_, stream_);
     std::swap(A_.cur, A_.alt);
-    launches_ += 5;
+    launches_ += 2;
     prof_mark();
     CK(cudaEventRecord(ev_consumed_, stream_));
     if (halo_valid_) {
@@ -1070,13 +1124,40 @@ template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int
     A_.step = (uint64_t)step_index;
     mark();
     if (P_.neigh_mode == T2D_NEIGH_EUCLID) {
-        if (use_fast2_ && Launch<R>::step_fast2(A_, moving, sm_count_, stream_))
+        if (const char* e = getenv("T2D_F2_ABLATE_AFTER")) {   // dev: ablation timing, see step_fast2.cuh
+            static int n_launch = 0;
+            const char* m = getenv("T2D_F2_ABLATE_MODE");
+            A_.ablate = (++n_launch > atoi(e)) ? (m ? atoi(m) : 0) : 0;
+        }
+        // lean pipeline (fp32 fast path, single context): the step kernel writes records, the sort moves record + aux only;
+        // pos / uv / r_dot / colour are rebuilt by materialize() when somebody asks for them
+        const bool lean = moving && use_fast2_ && lean_ok_ && !comm_on_;
+        if (!moving) materialize();   // t2d_forces reports through the full state
+        A_.lean = lean ? 1 : 0;
+        bool ran_fast2 = false;
+        if (use_fast2_ && Launch<R>::step_fast2(A_, moving, sm_count_, stream_)) {
             A_.queue_flip ^= 1;
-        else
+            ran_fast2 = true;
+        } else {
+            materialize();
+            A_.lean = 0;
             Launch<R>::step_euclid(A_, moving, stream_);   // cur -> alt (+ next keys)
+        }
         launches_++;
         mark();
         if (moving) std::swap(A_.cur, A_.alt);
+        if (moving && lean && ran_fast2) {
+            scan_buckets();
+            mark();
+            Launch<R>::scatter_lean(A_, stream_);
+            std::swap(A_.cur, A_.alt);
+            launches_++;
+            mark();
+            lean_ = true;
+            step_index++;
+            steps_++;
+            return;
+        }
     } else {
         Launch<R>::neigh_table(A_, stream_, sm_count_);
         launches_++;
@@ -1088,14 +1169,14 @@ template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int
         }
     }
     if (moving) {
-        launch_scan(A_.count, A_.start, A_.blocksums, A_.M, stream_);
-        launches_ += 3;
+        scan_buckets();
         mark();
         l2_window(A_.alt.pos);
         Launch<R>::scatter(A_, stream_);
         std::swap(A_.cur, A_.alt);
         launches_++;
         mark();
+        lean_ = false;
         step_index++;
         steps_++;
     }
@@ -1194,6 +1275,7 @@ template <typename R> int Engine<R>::forces(double* F, int* new_heading, int* co
 template <typename R> int Engine<R>::observables(double* out)
 {
     CK(cudaSetDevice(device_));
+    materialize();
     launch_observables(A_.cur.pos, A_.cur.rdot, comm_on_ ? A_.cur.aux : nullptr, sizeof(R) == 4, comm_on_ ? capacity_ : this->N,
                        comm_on_ ? &comm_state_.p->n : nullptr, d_trig_d_.p, d_obs_.p, stream_);
     launches_++;
@@ -1249,6 +1331,7 @@ template <typename R> int Engine<R>::get_r3d(int N, const double* uv, double* r3
 {
     if (N < 0 || N > capacity_) throw CudaError{"N exceeds the context's capacity"};
     CK(cudaSetDevice(device_));
+    materialize();
     StepArgs<R> T = A_;
     T.N = N;
     T.comm.on = 0;
@@ -1275,6 +1358,7 @@ template <typename R> int Engine<R>::tiling(int N, double* uv_old, double* uv, i
 {
     if (N < 0 || N > capacity_) throw CudaError{"N exceeds the context's capacity"};
     CK(cudaSetDevice(device_));
+    materialize();
     unsigned char* base = d_stage_in_.p;
     double* s_old = (double*)base;
     double* s_new = (double*)(base + 16 * (size_t)N);

@@ -138,6 +138,90 @@ void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The same scan in ONE launch (decoupled look-back): a tile publishes {launch number, state, value} as one 64-bit word —
+// state 1 = the tile's own sum, 2 = its inclusive prefix — and looks back over its predecessors' words until it meets an
+// inclusive one.  Tiles are numbered by a ticket counter in the order they start running, so a tile only ever waits for
+// tiles that are already resident; the launch number in the word makes resetting the status array unnecessary, and
+// `ticket_base` (the counter's value before this launch, tracked by the host) does the same for the counter.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(int* __restrict__ count, int* __restrict__ start,
+                                                               unsigned long long* status, int* ticket, int ticket_base, unsigned seq,
+                                                               int M, int nb)
+{
+    __shared__ int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1) - ticket_base;
+    __syncthreads();
+    const int tile = s_tile;
+    int4 q[SCAN_VEC];
+    tile_load(count, M, tile, q);
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_VEC; ++k) v += q[k].x + q[k].y + q[k].z + q[k].w;
+    int total;
+    block_incl_scan(v, &total);
+    volatile unsigned long long* st = status;
+    const unsigned long long tag = (unsigned long long)(seq & 0x3fffffffu) << 34;
+    if (threadIdx.x == 0) st[tile] = tag | ((unsigned long long)(tile == 0 ? 2u : 1u) << 32) | (unsigned)total;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int excl = 0;
+        for (int base = tile - 1; base >= 0; base -= 32) {
+            const int idx = base - lane;
+            unsigned long long w = tag | (2ull << 32);   // before the first tile: inclusive, value 0
+            if (idx >= 0) {
+                do {
+                    w = st[idx];
+                } while ((w >> 34) != (tag >> 34) || ((w >> 32) & 3u) == 0u);
+            }
+            const unsigned incl = __ballot_sync(0xffffffffu, ((w >> 32) & 3u) == 2u);
+            const int last = incl ? __ffs(incl) - 1 : 31;   // nearest predecessor that already knows its inclusive prefix
+            int val = lane <= last ? (int)(unsigned)w : 0;
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+            excl += __shfl_sync(0xffffffffu, val, 0);
+            if (incl) break;
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            if (tile > 0) st[tile] = tag | (2ull << 32) | (unsigned)(excl + total);
+        }
+    }
+    __syncthreads();
+    int carry = s_prefix;
+#pragma unroll
+    for (int k = 0; k < SCAN_VEC; ++k) {
+        const int base = tile * SCAN_TILE + (k * SCAN_THREADS + threadIdx.x) * 4;
+        const int s = q[k].x + q[k].y + q[k].z + q[k].w;
+        int tot;
+        const int inc = block_incl_scan(s, &tot);
+        int4 o;
+        o.x = carry + inc - s;
+        o.y = o.x + q[k].x;
+        o.z = o.y + q[k].y;
+        o.w = o.z + q[k].z;
+        if (base + 3 < M) {
+            *reinterpret_cast<int4*>(start + base) = o;
+            *reinterpret_cast<int4*>(count + base) = make_int4(0, 0, 0, 0);
+        } else {
+            const int t[4] = {o.x, o.y, o.z, o.w};
+            for (int j = 0; j < 4; ++j)
+                if (base + j < M) {
+                    start[base + j] = t[j];
+                    count[base + j] = 0;
+                }
+        }
+        carry += tot;
+    }
+    if (tile == nb - 1 && threadIdx.x == 0) start[M] = carry;
+}
+
+void launch_scan_onepass(int* count, int* start, unsigned long long* status, int* ticket, int ticket_base, unsigned seq, int M,
+                         cudaStream_t s)
+{
+    const int nb = scan_blocks(M);
+    if (nb > 0) k_scan_onepass<<<nb, SCAN_THREADS, 0, s>>>(count, start, status, ticket, ticket_base, seq, M, nb);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // observables: sum cos n, sum sin n, sum |rdot| over the resident particles
 // ---------------------------------------------------------------------------------------------------
 template <typename R>

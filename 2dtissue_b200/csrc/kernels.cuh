@@ -303,10 +303,41 @@ template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<
     }
     if (a.alt.rec) {   // fp32 fast path: the 32-byte record the neighbour pass of the next step reads (t2d_internal.h)
         const int n = (int)P.w;
-        const int slot = (unsigned)n <= 360u ? n : 361;   // index into the shared-memory trig table of k_step_fast2, 361 = not in it
+        const int slot = (unsigned)n <= 360u ? n : 362;   // index into the shared-memory trig table of k_step_fast2, 362 = not in it
         a.alt.rec[2 * (size_t)s] = make_float4((float)P.x, (float)P.y, (float)P.z, __int_as_float(slot));
         a.alt.rec[2 * (size_t)s + 1] = make_float4((float)U.x, (float)U.y, __int_as_float((int)key), __int_as_float(n));
     }
+}
+
+// K2, lean pipeline of the fp32 fast path (single context): the step kernel left the new state as records (alt.rec) + aux,
+// r_dot and colour in pre-sort order.  Only what the next step reads is sorted: record (32 B) + aux (16 B), plus the
+// 4-byte source index through which k_expand finds r_dot / colour when a caller asks for them.
+static __global__ void __launch_bounds__(256) k_scatter_lean(StepArgs<float> a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const float4 r0 = a.cur.rec[2 * (size_t)i], r1 = a.cur.rec[2 * (size_t)i + 1];
+    const int key = __float_as_int(r1.z);
+    const int s = a.start[key] + (int)a.rank[i];
+    a.alt.rec[2 * (size_t)s] = r0;
+    a.alt.rec[2 * (size_t)s + 1] = r1;
+    a.alt.aux[s] = a.cur.aux[i];
+    a.src[s] = i;
+}
+// the full sorted state from the lean one: pos / uv from the record, r_dot / colour through the source index
+// (a.alt = the pre-sort side that the last step kernel wrote)
+static __global__ void __launch_bounds__(256) k_expand(StepArgs<float> a)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.N) return;
+    const float4 r0 = a.cur.rec[2 * (size_t)s], r1 = a.cur.rec[2 * (size_t)s + 1];
+    const Pos3<float> P = {r0.x, r0.y, r0.z, (float)__float_as_int(r1.w)};
+    const Real2<float> U = {r1.x, r1.y};
+    a.cur.pos[s] = P;
+    a.cur.uv[s] = U;
+    const int i = a.src[s];
+    a.cur.rdot[s] = a.alt.rdot[i];
+    a.cur.color[s] = a.alt.color[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -824,7 +855,8 @@ static __device__ __noinline__ int locate_face_argmin_f32(int V, int F, int G, c
 
 template <bool MOVING>
 __device__ __forceinline__ void fast_epilogue(const StepArgs<float>& a, int i, const int4 ai, const Real2<float> ui, const double2 own,
-                                              const PairAcc& acc, int color, int hits, unsigned& npairs, unsigned& nties)
+                                              const PairAcc& acc, int color, int hits, unsigned& npairs, unsigned& nties,
+                                              int old_cell = -1, float ox = 0.0f, float oy = 0.0f, float oz = 0.0f)
 {
     typedef float R;
     const float fx = acc.fx, fy = acc.fy;
@@ -895,12 +927,12 @@ __device__ __forceinline__ void fast_epilogue(const StepArgs<float>& a, int i, c
                                     a.mesh.lift_mode == T2D_LIFT_BARYCENTRIC);
     const int vid = which == 0 ? tv.x : (which == 1 ? tv.y : tv.z);
     const Pos3<R> X = {Xv[0], Xv[1], Xv[2], (R)n_new};
-    a.alt.pos[i] = X;
-    a.alt.uv[i] = p;
     a.alt.aux[i] = make_int4(vid, f, ai.z, ai.w);
     a.alt.rdot[i] = rd;
     a.alt.color[i] = color;
     if (a.comm.on) {   // slab mode: stays / migrates / halo copy, messages, key
+        a.alt.pos[i] = X;
+        a.alt.uv[i] = p;
         BlockCounters sbc;
         slab_classify<R>(a, a.alt, i, X, p, rd, make_int4(vid, f, ai.z, ai.w), color, sbc);
         if (sbc.fault) atomicOr(&a.counters->fault, sbc.fault);
@@ -908,12 +940,29 @@ __device__ __forceinline__ void fast_epilogue(const StepArgs<float>& a, int i, c
     } else {
         int c[3];
         cell_coords<R>(a.vox, X, c);
-        int idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
-        if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket
-            atomicAdd(&a.counters->cell_fallbacks, 1ull);
-            idx = a.vox.M;
+        int idx = old_cell;
+        bool same = false;
+        if ((unsigned)old_cell < (unsigned)a.vox.M) {   // a particle moves ~1 % of a cell per step: same cell coordinates as before
+            const Pos3<R> O = {ox, oy, oz, 0.0f};       // -> same compact cell, without the row-word lookup (a scattered 8-byte
+            int c0[3];                                  // read in a table of several hundred MB: one DRAM sector per particle)
+            cell_coords<R>(a.vox, O, c0);
+            same = c[0] == c0[0] && c[1] == c0[1] && c[2] == c0[2];
         }
-        a.key[i] = (uint32_t)idx;
+        if (!same) {
+            idx = vox_index<R>(a.vox, c[0], c[1], c[2]);
+            if (idx < 0) {   // not in the static index (cannot happen for points on the mesh): overflow bucket
+                atomicAdd(&a.counters->cell_fallbacks, 1ull);
+                idx = a.vox.M;
+            }
+        }
+        if (a.lean) {   // lean pipeline (api.cu): the new state leaves as the 32-byte record the sort and the next step read
+            a.alt.rec[2 * (size_t)i] = make_float4(X.x, X.y, X.z, __int_as_float((unsigned)n_new <= 360u ? n_new : 362));
+            a.alt.rec[2 * (size_t)i + 1] = make_float4(p.x, p.y, __int_as_float(idx), __int_as_float(n_new));
+        } else {
+            a.alt.pos[i] = X;
+            a.alt.uv[i] = p;
+            a.key[i] = (uint32_t)idx;
+        }
         a.rank[i] = (uint32_t)atomicAdd(&a.count[idx], 1);
     }
 }
@@ -1507,6 +1556,18 @@ template <typename R> void Launch<R>::scatter(const StepArgs<R>& a, cudaStream_t
 {
     const int n = launch_extent<R>(a);
     if (n > 0) k_scatter<R><<<div_up(n, 256), 256, 0, s>>>(a);
+}
+template <typename R> void Launch<R>::scatter_lean(const StepArgs<R>& a, cudaStream_t s)
+{
+    if constexpr (sizeof(R) == 4) {
+        if (a.N > 0) k_scatter_lean<<<div_up(a.N, 256), 256, 0, s>>>(a);
+    }
+}
+template <typename R> void Launch<R>::expand(const StepArgs<R>& a, cudaStream_t s)
+{
+    if constexpr (sizeof(R) == 4) {
+        if (a.N > 0) k_expand<<<div_up(a.N, 256), 256, 0, s>>>(a);
+    }
 }
 template <typename R> void Launch<R>::step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s)
 {

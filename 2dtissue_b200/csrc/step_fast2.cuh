@@ -28,10 +28,22 @@ constexpr int F2_THREADS = 128;
 #define T2D_F2_MIN_BLOCKS 8
 #endif
 #ifndef T2D_F2_GRAB
-#define T2D_F2_GRAB 2   // consecutive 32-slot chunks per queue grab (the second chunk finds most of its candidates in L1)
+#define T2D_F2_GRAB 1   // consecutive 32-slot rows per queue ticket (measured: 1 -> 0.329 ms, 2 -> 0.362 ms, 4 -> 0.409 ms: the tail wins)
 #endif
 #ifndef T2D_F2_UNROLL
 #define T2D_F2_UNROLL 4
+#endif
+#ifndef T2D_F2_REVERSE
+#define T2D_F2_REVERSE 0   // 1: walk the slots from the end (what the scatter wrote last is still in L2)
+#endif
+#ifndef T2D_F2_L2PF
+#define T2D_F2_L2PF 0      // > 0: every grab asks the TMA unit to prefetch the records of the grab this many grabs ahead into L2
+#endif
+#ifndef T2D_F2_PFD
+#define T2D_F2_PFD 0       // > 0: every trip prefetches (L1) the records this many trips ahead; range starts prefetch the next range
+#endif
+#ifndef T2D_F2_LD128
+#define T2D_F2_LD128 0     // 1: candidates are read as LDG.128 {x, y, z, slot} + a predicated LDG.64 {u, v} instead of one LDG.256
 #endif
 constexpr int F2_TRIG_N = 361;   // headings 0..360: what alignment produces (OrientationHelper.cpp:102-116); seam re-entry makes the rest
 constexpr unsigned F2_TIE_ULPS = 8;
@@ -97,6 +109,20 @@ __device__ __forceinline__ F2Rec f2_load(const float4* __restrict__ q)
         : "l"(q));
     return r;
 }
+// candidate variant: first half only; (u, v) is fetched by f2_candidate when the pair is in range
+__device__ __forceinline__ F2Rec f2_load_half(const float4* __restrict__ q)
+{
+    F2Rec r;
+    asm("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=r"(r.slot) : "l"(q));
+    r.u = r.v = 0.0f;
+    r.cell = r.heading = 0;
+    return r;
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ double2 f2_lds_trig(uint32_t addr)
 {
     double2 t;
@@ -109,33 +135,66 @@ __device__ __forceinline__ double2 f2_lds_trig(uint32_t addr)
 // vector of the neighbour's heading from the shared-memory copy of the host-libm table, summed in double
 // (OrientationHelper.cpp:43-58).  About 56 % of the candidates are in range, so some lane of the warp needs the pair term
 // almost every time: it is computed for every candidate and masked — an out-of-range candidate reads the table's zero
-// entry (slot 362) and gets g = 0.  A heading outside the table has slot 361 (also zero); `oob` then sends the thread through
-// the rare global-table path after the group.  TIES: log candidates within F2_TIE_ULPS ulps of a squared cutoff — a
+// entry (slot 361) and gets g = 0.  A heading outside the table has slot 362 (also zero); `oobm` (the largest slot seen) then
+// sends the thread through the rare global-table path after the group.  TIES: log candidates within F2_TIE_ULPS ulps of a squared cutoff — a
 // neighbour-set or colour difference against the fp64 oracle must be one of these (tests/test_gpu_fastpath.py).
 template <bool TIES>
-__device__ __forceinline__ void f2_candidate(const F2Rec& J, const float px, const float py, const float pz, const float2 ui,
-                                             const F2Consts& k, const uint32_t s_trig, F2Acc& acc, bool& oob)
+__device__ __forceinline__ void f2_candidate(const F2Rec& J, const float4* __restrict__ q, const float px, const float py,
+                                             const float pz, const float2 ui, const F2Consts& k, const uint32_t s_trig, F2Acc& acc,
+                                             unsigned& oobm)
 {
-    const float dx = px - J.x, dy = py - J.y, dz = pz - J.z;
-    const float d2 = dx * dx + dy * dy + dz * dz;
-    const bool p = d2 < k.r2s, z = d2 == 0.0f;
-    acc.color += (d2 <= k.r2c && !z) ? 1 : 0;
+    // hand-scheduled PTX: 25 instructions per candidate, every value defined on every path (nothing for ptxas to spill or
+    // to turn into branches); slot 361 = zero entry for "not in range", 362 = zero entry for "heading not in the table"
+    float d2;
+    asm("{\n\t"
+        ".reg .pred p, nz, c;\n\t"
+        ".reg .f32 dx, dy, dz, inv, g, ux, uy;\n\t"
+        ".reg .u32 idx, ad;\n\t"
+        ".reg .f64 tc, ts;\n\t"
+        "sub.ftz.f32 dx, %8, %11;\n\t"
+        "sub.ftz.f32 dy, %9, %12;\n\t"
+        "sub.ftz.f32 dz, %10, %13;\n\t"
+        "mul.ftz.f32 %7, dx, dx;\n\t"
+        "fma.rn.ftz.f32 %7, dy, dy, %7;\n\t"
+        "fma.rn.ftz.f32 %7, dz, dz, %7;\n\t"
+        "setp.lt.ftz.f32 p, %7, %19;\n\t"
+#if T2D_F2_LD128
+        "mov.f32 ux, 0f00000000;\n\t"
+        "mov.f32 uy, 0f00000000;\n\t"
+        "@p ld.global.nc.v2.f32 {ux, uy}, [%24+16];\n\t"
+#endif
+        "setp.neu.ftz.f32 nz, %7, 0f00000000;\n\t"
+        "setp.le.and.ftz.f32 c, %7, %20, nz;\n\t"
+        "@c add.s32 %4, %4, 1;\n\t"
+        "@p add.s32 %5, %5, 1;\n\t"
+        "selp.u32 idx, %14, 361, p;\n\t"
+        "max.u32 %6, %6, idx;\n\t"
+        "shl.b32 ad, idx, 4;\n\t"
+        "add.u32 ad, ad, %23;\n\t"
+        "ld.shared.v2.f64 {tc, ts}, [ad];\n\t"
+        "rsqrt.approx.ftz.f32 inv, %7;\n\t"
+        "selp.f32 inv, inv, 0f447A0000, nz;\n\t"
+        "fma.rn.ftz.f32 g, inv, %21, %22;\n\t"
+        "selp.f32 g, g, 0f00000000, p;\n\t"
+#if T2D_F2_LD128
+        "sub.ftz.f32 ux, %17, ux;\n\t"
+        "sub.ftz.f32 uy, %18, uy;\n\t"
+#else
+        "sub.ftz.f32 ux, %17, %15;\n\t"
+        "sub.ftz.f32 uy, %18, %16;\n\t"
+#endif
+        "fma.rn.ftz.f32 %0, g, ux, %0;\n\t"
+        "fma.rn.ftz.f32 %1, g, uy, %1;\n\t"
+        "add.f64 %2, %2, tc;\n\t"
+        "add.f64 %3, %3, ts;\n\t"
+        "}"
+        : "+f"(acc.fx), "+f"(acc.fy), "+d"(acc.mx), "+d"(acc.my), "+r"(acc.color), "+r"(acc.hits), "+r"(oobm), "=f"(d2)
+        : "f"(px), "f"(py), "f"(pz), "f"(J.x), "f"(J.y), "f"(J.z), "r"(J.slot), "f"(J.u), "f"(J.v), "f"(ui.x), "f"(ui.y),
+          "f"(k.r2s), "f"(k.r2c), "f"(k.g1), "f"(k.g0), "r"(s_trig), "l"(q));
     if (TIES) {
         const unsigned bm1 = __float_as_uint(d2) - 1u;
         if ((bm1 - k.tie_s_lo) <= 2u * F2_TIE_ULPS || (bm1 - k.tie_c_lo) <= 2u * F2_TIE_ULPS) acc.ties++;
     }
-    const unsigned idx = p ? J.slot : (unsigned)(F2_TRIG_N + 1);
-    const double2 tr = f2_lds_trig(s_trig + idx * 16u);
-    acc.mx += tr.x;
-    acc.my += tr.y;
-    float inv = rsqrtf(d2);
-    inv = z ? 1000.0f : inv;
-    float g = fmaf(inv, k.g1, k.g0);
-    g = p ? g : 0.0f;
-    acc.fx = fmaf(g, ui.x - J.u, acc.fx);
-    acc.fy = fmaf(g, ui.y - J.v, acc.fy);
-    acc.hits += p ? 1 : 0;
-    oob = oob || idx == (unsigned)F2_TRIG_N;
 }
 // the rare path: an in-range neighbour whose heading is outside 0..360 (it crossed the seam in the last step)
 template <int = 0>
@@ -144,9 +203,37 @@ __device__ __noinline__ double2 f2_oob_term(const double2* g_trig, float r2s, fl
 {
     const float dx = px - jx, dy = py - jy, dz = pz - jz;
     const float d2 = dx * dx + dy * dy + dz * dz;
-    if (!(d2 < r2s) || slot != (unsigned)F2_TRIG_N) return make_double2(0.0, 0.0);
+    if (!(d2 < r2s) || slot != (unsigned)(F2_TRIG_N + 1)) return make_double2(0.0, 0.0);
     unsigned long long fb = 0;
     return trig_lookup(g_trig, heading, fb);
+}
+
+// One trip of the candidate loop: T2D_F2_UNROLL records loaded together, then their candidate blocks (which ptxas interleaves).
+// MASKED: only the first `cnt` records exist; the others are read from the sentinel record (far away, zero trig slot).
+template <bool TIES, bool MASKED>
+__device__ __forceinline__ void f2_trip(const float4* __restrict__ q, int cnt, const float4* __restrict__ sent,
+                                        const double2* __restrict__ g_trig, const float px, const float py, const float pz,
+                                        const float2 ui, const F2Consts& k, const uint32_t s_trig, F2Acc& acc)
+{
+    F2Rec J[T2D_F2_UNROLL];
+    const float4* qu[T2D_F2_UNROLL];
+#pragma unroll
+    for (int u = 0; u < T2D_F2_UNROLL; ++u) {
+        qu[u] = (!MASKED || u < cnt) ? q + 2 * u : sent;
+        J[u] = T2D_F2_LD128 ? f2_load_half(qu[u]) : f2_load(qu[u]);
+    }
+    unsigned oob = 0;
+#pragma unroll
+    for (int u = 0; u < T2D_F2_UNROLL; ++u) f2_candidate<TIES>(J[u], qu[u], px, py, pz, ui, k, s_trig, acc, oob);
+    if (__builtin_expect(oob > (unsigned)F2_TRIG_N, 0)) {
+#pragma unroll 1
+        for (int u = 0; u < (MASKED ? cnt : T2D_F2_UNROLL); ++u) {
+            const F2Rec O = f2_load(q + 2 * u);
+            const double2 tr = f2_oob_term(g_trig, k.r2s, px, py, pz, O.x, O.y, O.z, O.slot, O.heading);
+            acc.mx += tr.x;
+            acc.my += tr.y;
+        }
+    }
 }
 
 // a particle outside the static index (overflow bucket; cannot happen for points on the mesh): its ranges from its coordinates,
@@ -202,21 +289,43 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
     const int ngrabs = (nres + 32 * T2D_F2_GRAB - 1) / (32 * T2D_F2_GRAB);
     const int M = a.vox.M;
     const float4* __restrict__ rec = a.cur.rec;
+    const float4* __restrict__ sent = a.rec_sentinel;
     const int* __restrict__ start = a.start;
     const int ob = start[M], ol = start[M + 1] - ob;   // overflow bucket: normally empty
     unsigned npairs_w = 0, nties_w = 0, ncut_w = 0, fb_w = 0;
 
+#ifndef T2D_F2_STATIC
+#define T2D_F2_STATIC 0   // 1: rows are dealt round-robin to the resident warps (no queue); 2: queue per 16-row block, rows inside it static
+#endif
     int next = 0;
+#if T2D_F2_STATIC == 1
+    next = blockIdx.x * (F2_THREADS / 32) + (tid >> 5);
+#else
     if (lane == 0) next = atomicAdd(queue, 1);
+#endif
     mbar_wait(&sm.bar, 0);   // the table has landed (every thread observes the barrier itself)
     if (tid < 2) sm.trig[F2_TRIG_N + tid] = make_double2(0.0, 0.0);
     __syncthreads();
     const uint32_t s_trig = smem_u32(sm.trig);
 
     for (;;) {
-        const int grab = __shfl_sync(0xffffffffu, next, 0);
-        if (grab >= ngrabs) break;
+        const int ticket = __shfl_sync(0xffffffffu, next, 0);
+        if (ticket >= ngrabs) break;
+#if T2D_F2_STATIC == 1
+        next += gridDim.x * (F2_THREADS / 32);
+#else
         if (lane == 0) next = atomicAdd(queue, 1);   // in flight while this grab is processed
+#endif
+        const int grab = T2D_F2_REVERSE ? ngrabs - 1 - ticket : ticket;
+#if T2D_F2_L2PF > 0
+        if (lane == 0) {   // ask the TMA unit to bring the records of a later grab into L2 (no register, no scoreboard)
+            const int ahead = T2D_F2_REVERSE ? grab - T2D_F2_L2PF : grab + T2D_F2_L2PF;
+            if (ahead >= 0 && (ahead + 1) * 32 * T2D_F2_GRAB <= nres) {
+                bulk_prefetch_l2(rec + 2 * (size_t)ahead * 32 * T2D_F2_GRAB, 32u * 32u * T2D_F2_GRAB);
+                bulk_prefetch_l2(a.cur.aux + (size_t)ahead * 32 * T2D_F2_GRAB, 16u * 32u * T2D_F2_GRAB);
+            }
+        }
+#endif
 #pragma unroll 1
         for (int sub = 0; sub < T2D_F2_GRAB; ++sub) {
             const int i = (grab * T2D_F2_GRAB + sub) * 32 + lane;
@@ -229,14 +338,25 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
             }
             F2Acc acc;
             float2 ui = make_float2(0.0f, 0.0f);
-            int nh = 0;
+            int nh = 0, own_cell = -1;
+            float ox = 0.0f, oy = 0.0f, oz = 0.0f;
             if (live) {
                 const F2Rec self = f2_load(rec + 2 * (size_t)i);
                 const float px = self.x, py = self.y, pz = self.z;
                 nh = self.heading;
                 ui = make_float2(self.u, self.v);
                 const int cell = self.cell;
+                own_cell = cell;
+                ox = px;
+                oy = py;
+                oz = pz;
                 int key[9];
+#ifdef T2D_F2_ABLATE
+                if (a.ablate == 5) {
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) key[m] = m;
+                } else
+#endif
                 if (cell < M) {
                     const int4* nb = reinterpret_cast<const int4*>(a.nbr + (size_t)cell * NBR_STRIDE);
                     int4 q[5];
@@ -278,6 +398,9 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
                     sm.rkey[m][tid] = key[m];
                     nr += key[m] >= 16 ? 1 : 0;
                 }
+#ifdef T2D_F2_ABLATE
+                if (a.ablate == 1 || a.ablate == 4) nr = 0;   // dev: no candidate loop
+#endif
                 if (ol > 0) {   // the overflow bucket is everybody's candidate
                     sm.rbeg[9][tid] = ob;
                     sm.rkey[nr][tid] = (min(ol, 0x07ffffff) << 4) | 9;
@@ -285,40 +408,44 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
                 }
 #pragma unroll 1
                 for (int m = 0; m < nr; ++m) {
+#ifdef T2D_F2_ABLATE
+                    if (a.ablate == 3) {   // dev: loads only
+                        const int kk2 = sm.rkey[m][tid];
+                        const float4* q2 = rec + 2 * (size_t)sm.rbeg[kk2 & 15][tid];
+                        for (int t2 = 0; t2 < (kk2 >> 4); t2 += 4) {
+                            const F2Rec a0 = f2_load(q2 + 2 * t2), a1 = f2_load(q2 + 2 * min(t2 + 1, (kk2 >> 4) - 1)),
+                                        a2 = f2_load(q2 + 2 * min(t2 + 2, (kk2 >> 4) - 1)), a3 = f2_load(q2 + 2 * min(t2 + 3, (kk2 >> 4) - 1));
+                            acc.fx += a0.x + a1.y + a2.z + a3.u;
+                        }
+                        continue;
+                    }
+#endif
                     const int kk = sm.rkey[m][tid];
                     const int len = kk >> 4, jb = sm.rbeg[kk & 15][tid];
                     const float4* q = rec + 2 * (size_t)jb;
+#ifdef T2D_F2_ABLATE
+                    if (a.ablate == 6) q = rec + 2 * (size_t)max(0, min(i - lane, nres - 4 - len));   // dev: every candidate load hits L1
+#endif
                     int t = 0;
-#if T2D_F2_UNROLL > 1
-                    for (; t + T2D_F2_UNROLL <= len; t += T2D_F2_UNROLL, q += 2 * T2D_F2_UNROLL) {
-                        F2Rec J[T2D_F2_UNROLL];
-#pragma unroll
-                        for (int u = 0; u < T2D_F2_UNROLL; ++u) J[u] = f2_load(q + 2 * u);
-                        bool oob = false;
-#pragma unroll
-                        for (int u = 0; u < T2D_F2_UNROLL; ++u) f2_candidate<TIES>(J[u], px, py, pz, ui, k, s_trig, acc, oob);
-                        if (__builtin_expect(oob, 0)) {
-#pragma unroll 1
-                            for (int u = 0; u < T2D_F2_UNROLL; ++u) {
-                                const F2Rec O = f2_load(q + 2 * u);
-                                const double2 tr = f2_oob_term(a.trig_d, k.r2s, px, py, pz, O.x, O.y, O.z, O.slot, O.heading);
-                                acc.mx += tr.x;
-                                acc.my += tr.y;
-                            }
-                        }
+#if T2D_F2_PFD > 0
+                    if (m + 1 < nr) {   // the first two trips of the NEXT range (the trips below prefetch within this one)
+                        const int kn = sm.rkey[m + 1][tid];
+                        const float4* qn = rec + 2 * (size_t)sm.rbeg[kn & 15][tid];
+                        prefetch_l1(qn);
+                        prefetch_l1(qn + 4);
+                        if ((kn >> 4) > 4) prefetch_l1(qn + 8);
                     }
 #endif
-#pragma unroll 1
-                    for (; t < len; ++t, q += 2) {
-                        const F2Rec J = f2_load(q);
-                        bool oob = false;
-                        f2_candidate<TIES>(J, px, py, pz, ui, k, s_trig, acc, oob);
-                        if (__builtin_expect(oob, 0)) {
-                            const double2 tr = f2_oob_term(a.trig_d, k.r2s, px, py, pz, J.x, J.y, J.z, J.slot, J.heading);
-                            acc.mx += tr.x;
-                            acc.my += tr.y;
-                        }
+                    for (; t + T2D_F2_UNROLL <= len; t += T2D_F2_UNROLL, q += 2 * T2D_F2_UNROLL) {
+#if T2D_F2_PFD > 0
+                        prefetch_l1(q + 2 * T2D_F2_UNROLL * T2D_F2_PFD);
+                        prefetch_l1(q + 2 * T2D_F2_UNROLL * T2D_F2_PFD + 2 * T2D_F2_UNROLL - 2);
+#endif
+                        f2_trip<TIES, false>(q, T2D_F2_UNROLL, sent, a.trig_d, px, py, pz, ui, k, s_trig, acc);
                     }
+                    // the rest of the range as ONE masked trip (the candidates beyond the end read the sentinel record): a
+                    // one-candidate-per-trip remainder loop had 38 % of the kernel's load waits for 13 % of its candidates
+                    if (t < len) f2_trip<TIES, true>(q, len - t, sent, a.trig_d, px, py, pz, ui, k, s_trig, acc);
                 }
             }
             __syncwarp();   // reconverge: lanes leave the candidate loops at different times, the tail is the same for all
@@ -338,7 +465,21 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
                 pa.mx = acc.mx;
                 pa.my = acc.my;
                 Real2<R> uir = {ui.x, ui.y};
-                fast_epilogue<MOVING>(a, i, ai, uir, own, pa, acc.color, acc.hits, npairs, nties);
+#ifdef T2D_F2_ABLATE
+                if (a.ablate == 2 || a.ablate == 4) {   // dev: no epilogue — the state is copied through unchanged (valid input for the sort)
+                    const Pos3<R> X = {ox, oy, oz, (R)nh};
+                    a.alt.pos[i] = X;
+                    a.alt.uv[i] = uir;
+                    a.alt.aux[i] = ai;
+                    Real2<R> rd = {pa.fx + (float)own.x, pa.fy + (float)(pa.mx + pa.my)};
+                    a.alt.rdot[i] = rd;
+                    a.alt.color[i] = acc.color + acc.hits;
+                    a.key[i] = (uint32_t)own_cell;
+                    a.rank[i] = (uint32_t)atomicAdd(&a.count[own_cell], 1);
+                    continue;
+                }
+#endif
+                fast_epilogue<MOVING>(a, i, ai, uir, own, pa, acc.color, acc.hits, npairs, nties, own_cell, ox, oy, oz);
             }
             npairs_w += npairs;
             nties_w += nties;
@@ -361,7 +502,7 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
 template <typename R> bool Launch<R>::step_fast2(const StepArgs<R>& a, bool moving, int sm_count, cudaStream_t s)
 {
     if constexpr (sizeof(R) == 4) {
-        if (!a.cur.rec || !a.nbr) return false;
+        if (!a.cur.rec || !a.nbr || !a.rec_sentinel) return false;
         const int n = a.comm.on ? a.comm.capacity : a.N;
         if (n <= 0) return true;
         const int ngrabs = div_up(n, 32 * T2D_F2_GRAB);

@@ -152,6 +152,10 @@ template <typename R> struct StepArgs {
     int write_F;
     int count_ties = 1;            // fp32 fast path: log candidates within 8 ulps of a cutoff in ties_cutoff
     int* work_counter = nullptr;   // [4] dynamic queues: [0] buckets of the table-mode kernel, [1], [2] chunk queues of k_step_fast2
+    const float4* rec_sentinel = nullptr;   // one record that is nobody's neighbour: what the masked tail trips of k_step_fast2 read
+    int* src = nullptr;            // lean pipeline: sorted slot -> index in the pre-sort arrays (r_dot, colour)
+    int lean = 0;                  // 1: k_step_fast2 writes records (alt.rec) instead of pos / uv / key (single context, fp32 Euclid)
+    int ablate = 0;                // dev builds (-DT2D_F2_ABLATE) only: 1 no candidate loop, 2 no epilogue, 3 loads only
     int queue_flip = 0;            // which of the two chunk queues the next k_step_fast2 launch uses (it zeroes the other one)
 };
 
@@ -161,6 +165,8 @@ template <typename R> struct Launch {
                          unsigned* occ, cudaStream_t s);   // setup: surface cells of the sparse row index
     static void bin(const StepArgs<R>& a, cudaStream_t s);                      // key + rank + histogram of `cur`
     static void scatter(const StepArgs<R>& a, cudaStream_t s);                  // cur -> alt in bucket order
+    static void scatter_lean(const StepArgs<R>& a, cudaStream_t s);             // fp32 fast path: records + aux + source index only
+    static void expand(const StepArgs<R>& a, cudaStream_t s);                   // fp32 fast path: lean state -> pos / uv / r_dot / colour
     static void step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s); // stages 2-5 fused, cur -> alt (+ next keys)
     static bool step_fast2(const StepArgs<R>& a, bool moving, int sm_count, cudaStream_t s);   // fp32 only (step_fast2.cuh); false = not available
     static void build_nbr(const DevVox<R>& vx, int2* nbr, cudaStream_t s);      // setup: static neighbourhood table
@@ -179,6 +185,8 @@ template <typename R> struct Launch {
 // precision-independent kernels (common.cu)
 void launch_scan(int* count, int* start, int* blocksums, int M, cudaStream_t s);   // exclusive scan, zeroes count
 int scan_blocks(int M);
+void launch_scan_onepass(int* count, int* start, unsigned long long* status, int* ticket, int ticket_base, unsigned seq, int M,
+                         cudaStream_t s);   // the same in one launch (decoupled look-back); status: [scan_blocks(M)] words
 void launch_observables(const void* pos, const void* rdot, const int4* aux, int is_f32, int N, const int* dN,
                         const double2* trig, double* out8, cudaStream_t s);   // aux/dN: slab mode (skip halo copies, device count)
 

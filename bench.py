@@ -9,6 +9,8 @@ re-projection) over all resident particles.  Workload (config.workload):
     c4shard  (default) the per-GPU shard of BASELINE.json configs[3]: 2M particles per GPU (16M on 8 GPUs), refined
              ("high-resolution") ellipsoid chart, Euclidean neighbour cutoff, fp32 fast path, weak scaling
     c2       configs[1]: 10k particles, Euclidean cutoff        c3  configs[2]: 1M particles, table criterion
+    c5       configs[4]: noise sweep (order-parameter phase diagram): every GPU runs independent 1M-particle replicas,
+             each with its own noise amplitude eta and seed; no communication; phi(eta) and mean speed in the JSON line
 One JSON line is printed by rank 0.  `value` = whole-job particle-steps/s with the state resident in HBM;
 `e2e` = the same metric through t2d_step_host() with pinned HOST buffers (H2D + step + D2H every step).
 """
@@ -116,6 +118,11 @@ def workload_spec(args, world):
     if w == "c3":
         return dict(name="c3: 1M particles, ellipsoid_x4 chart, hop-count vertex-distance table", per_gpu=1_000_000,
                     total=1_000_000 * world, mode="table", refine=0, dtype=args.dtype or "f32")
+    if w == "c5":
+        per = args.particles_per_gpu or 1_000_000
+        return dict(name="c5: noise sweep, %d independent replica(s) of %d particles, one per GPU, eta = k/(R-1) (R > 1) or 0.25, "
+                         "ellipsoid chart refined 2 levels, Euclidean cutoff" % (world, per),
+                    per_gpu=per, total=per * world, mode="euclid", refine=2, dtype=args.dtype or "f32", replicas=True)
     raise SystemExit("unknown workload " + w)
 
 
@@ -133,13 +140,61 @@ def load_chart(t2d, refine):
 # ------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path, bounded sample
 # ------------------------------------------------------------------------------------------------------
-def run_reference_sample(spec, steps, warmup, seconds_budget=25.0):
-    """Returns (particle_steps_per_s, cores, kind, sample_text)."""
+def run_port_same_config(spec, steps, warmup, seconds_budget=60.0):
+    """The CPU comparator on OUR arm's configuration: the O(N k) OpenMP restatement of the reference's step
+    (oracle/t2d_oracle.c, bit-identical to the compiled reference on every golden fixture) on the same chart, sigma,
+    particle count and seeded state as the GPU arm, all host threads, as many steps as fit the time budget.
+    Returns a cpu_baseline dict (kind "port")."""
     t2d = importlib.import_module("2dtissue_b200")
-    chart = load_chart(t2d, 0)   # the compiled reference walks ALL faces per particle: keep its own mesh
-    from oracle import refbind, oraclebind
+    from oracle import oraclebind
     mode = 1 if spec["mode"] == "euclid" else 0
-    if refbind.available():
+    N = spec["per_gpu"] if spec.get("replicas") else spec["total"]
+    chart = load_chart(t2d, spec["refine"])
+    orc = oraclebind.Oracle(chart)
+    if mode == 0:
+        orc.set_table(orc.build_hop_table())
+    sigma = sigma_for(N) if mode == 1 else 0.4166666666666667
+    eta = 0.25 if spec.get("replicas") else 0.0
+    uv, n = t2d.seed_particles(N, seed=1234)
+    r3d, vid, _ = orc.get_r3d(uv)
+    st = dict(uv=uv, n=n, vid=vid, r3d=r3d)
+    cores = os.cpu_count() or 1
+    t_start = time.perf_counter()
+    done_w = 0
+    for _ in range(max(1, warmup)):   # untimed; cut short if one step already eats a third of the budget
+        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, eta=eta, seed=1234, mode=mode, threads=cores,
+                      step_index=done_w)
+        done_w += 1
+        if time.perf_counter() - t_start > seconds_budget / 3:
+            break
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(max(1, steps)):
+        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, eta=eta, seed=1234, mode=mode, threads=cores,
+                      step_index=done_w + done)
+        done += 1
+        if time.perf_counter() - t_start > seconds_budget:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": N * done / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": ("same configuration as the GPU arm (%s): %d particles, sigma %.6g, %d-face chart, seeded state; O(N k) cell-list "
+                       "restatement of the reference's step (oracle/t2d_oracle.c, OpenMP, %d threads), %d warm-up + %d timed steps"
+                       % (spec["mode"], N, sigma, len(chart["faces"]), cores, done_w, done)),
+            "same_config": True, "fault": int(st["fault"])}
+
+
+def run_compiled_reference(spec, seconds_budget=8.0):
+    """The UNMODIFIED compiled reference (oracle/_ref).  It is O(N^2) in time and memory and single-threaded, so it cannot
+    hold the bench configuration: 1500 particles on its own unrefined chart.  In Euclid mode the harness feeds the
+    reference's ForceHelper / OrientationHelper classes a Euclidean dist_length (the reference has no Euclid mode, so this
+    is not simulate_flight end to end); in table mode it is the reference's simulate_flight."""
+    try:
+        from oracle import refbind, oraclebind
+        if not refbind.available():
+            return {"unavailable": "oracle/_ref is not built"}
+        t2d = importlib.import_module("2dtissue_b200")
+        chart = load_chart(t2d, 0)
+        mode = 1 if spec["mode"] == "euclid" else 0
         ref = refbind.Ref()
         ref.chart_import(chart)
         if mode == 0:
@@ -149,65 +204,22 @@ def run_reference_sample(spec, steps, warmup, seconds_budget=25.0):
         uv, n = t2d.seed_particles(Ns, seed=1234)
         r3d, vid = ref.get_r3d(uv)
         st = dict(uv=uv, n=n, vid=vid, r3d=r3d)
-        for _ in range(max(1, min(warmup, 1))):
-            st = ref.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode)
+        st = ref.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode)
         t0 = time.perf_counter()
         done = 0
-        for _ in range(steps):
+        while done < 50:
             st = ref.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode)
             done += 1
             if time.perf_counter() - t0 > seconds_budget:
                 break
         dt = time.perf_counter() - t0
-        return Ns * done / dt, 1, "reference", ("compiled reference (oracle/_ref), single thread (it has none), %d particles x %d "
-                                               "steps on ellipsoid_x4, %s criterion; O(N^2): cannot hold the full workload" %
-                                               (Ns, done, spec["mode"]))
-    orc = oraclebind.Oracle(chart)
-    if mode == 0:
-        orc.set_table(orc.build_hop_table())
-    Ns = 200_000 if mode == 1 else 50_000
-    sigma = sigma_for(Ns) if mode == 1 else 0.4166666666666667
-    uv, n = t2d.seed_particles(Ns, seed=1234)
-    r3d, vid, _ = orc.get_r3d(uv)
-    st = dict(uv=uv, n=n, vid=vid, r3d=r3d)
-    cores = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    done = 0
-    for _ in range(steps):
-        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode, threads=cores)
-        done += 1
-        if time.perf_counter() - t0 > seconds_budget:
-            break
-    dt = time.perf_counter() - t0
-    return Ns * done / dt, cores, "port", "oracle port (OpenMP, %d threads), %d particles x %d steps" % (cores, Ns, done)
-
-
-def run_port_sample(spec, seconds_budget=8.0):
-    """The O(N k) CPU restatement (oracle/t2d_oracle.c, OpenMP over particles) on all host cores: what a CPU user would
-    get from the same algorithmic idea.  Returns a dict for cpu_baseline["port"], or None."""
-    try:
-        t2d = importlib.import_module("2dtissue_b200")
-        from oracle import oraclebind
-        chart = load_chart(t2d, 0)
-        mode = 1 if spec["mode"] == "euclid" else 0
-        orc = oraclebind.Oracle(chart)
-        if mode == 0:
-            orc.set_table(orc.build_hop_table())
-        Ns = 200_000 if mode == 1 else 50_000
-        sigma = sigma_for(Ns) if mode == 1 else 0.4166666666666667
-        uv, n = t2d.seed_particles(Ns, seed=1234)
-        r3d, vid, _ = orc.get_r3d(uv)
-        st = dict(uv=uv, n=n, vid=vid, r3d=r3d)
-        cores = os.cpu_count() or 1
-        t0 = time.perf_counter()
-        done = 0
-        while done < 3 and time.perf_counter() - t0 < seconds_budget:
-            st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, mode=mode, threads=cores)
-            done += 1
-        dt = time.perf_counter() - t0
-        return {"value": Ns * done / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-                "sample": "oracle port (O(N k) cell list, OpenMP, %d threads), %d particles x %d steps on ellipsoid_x4" % (cores, Ns, done)}
-    except Exception as e:   # the baseline is a report, never a reason to lose the GPU line
+        return {"value": Ns * done / dt, "unit": "particle-steps/s", "cores": 1, "kind": "reference", "same_config": False,
+                "sample": ("compiled reference (oracle/_ref), single thread (it has none), %d particles x %d steps on the unrefined "
+                           "ellipsoid_x4 chart, %s criterion%s; O(N^2) time and memory: cannot hold the bench configuration"
+                           % (Ns, done, spec["mode"],
+                              " (harness-built Euclidean dist_length into the reference's ForceHelper/OrientationHelper, not "
+                              "simulate_flight: the reference has no Euclid mode)" if mode == 1 else ""))}
+    except Exception as e:   # a report, never a reason to lose the line
         return {"unavailable": str(e)[:200]}
 
 
@@ -215,12 +227,14 @@ def main_reference(args, rank, world):
     if rank != 0:
         return
     spec = workload_spec(args, world)
-    v, cores, kind, sample = run_reference_sample(spec, args.steps, args.warmup)
+    cb = run_port_same_config(spec, args.steps, args.warmup, seconds_budget=90.0)
+    cb["reference_compiled"] = run_compiled_reference(spec)
+    v = cb["value"]
     line = {"impl": "reference", "metric": "particle_steps_per_sec", "value": v, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": spec["name"]},
-            "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": {"workload": spec["name"], "what_ran": cb["sample"]},
+            "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(json.dumps(line))
 
@@ -244,8 +258,9 @@ def main_ours(args, rank, world, local_rank):
     mode = t2d.NEIGH_EUCLID if spec["mode"] == "euclid" else t2d.NEIGH_TABLE
     prec = t2d.PRECISION_FP32 if spec["dtype"] == "f32" else t2d.PRECISION_FP64
     Nloc = spec["per_gpu"]
-    sigma = sigma_for(spec["total"]) if mode == t2d.NEIGH_EUCLID else 0.4166666666666667
-    slabs = world > 1
+    replicas = bool(spec.get("replicas"))            # c5: every rank is its own closed system
+    sigma = sigma_for(spec["per_gpu"] if replicas else spec["total"]) if mode == t2d.NEIGH_EUCLID else 0.4166666666666667
+    slabs = world > 1 and not replicas
     if slabs and mode != t2d.NEIGH_EUCLID:
         raise SystemExit("multi-GPU slabs support the Euclidean criterion (workloads c4shard / c2)")
     cap = int(Nloc * 1.25) + 65536 if slabs else Nloc      # room for halo copies and migration imbalance
@@ -255,9 +270,14 @@ def main_ours(args, rank, world, local_rank):
         spec["name"] += ", barycentric lift (extension, not the reference's semantics)"
     if mode == t2d.NEIGH_TABLE:
         kw["table_kind"] = t2d.TABLE_HOPS_FROM_MESH
+    eta, rep_seed = 0.0, 1234
+    if replicas:   # OrientationHelper.cpp:67-70: heading = int(mean angle + eta * 360 * (u - 0.5)), u from (seed, step, id)
+        eta = rank / (world - 1) if world > 1 else 0.25
+        rep_seed = 1234 + 1000 * rank
+        kw.update(eta=eta, seed=rep_seed)
     ctx = t2d.Context(chart, **kw)
     if not slabs:
-        uv, n = t2d.seed_particles(Nloc, seed=1234)
+        uv, n = t2d.seed_particles(Nloc, seed=rep_seed)
         ctx.set_particles(uv, n)
     else:
         # ONE global particle set (spec["total"]), seeded identically on every rank; every rank projects it on its own
@@ -322,9 +342,22 @@ def main_ours(args, rank, world, local_rank):
             prof.setdefault(name, []).append(ms)
     prof = {k: statistics.median(v) for k, v in prof.items()}
 
+    phase = None
+    if replicas:   # the phase diagram: relax every replica further (untimed), then read the polar order parameter
+        if args.relax_steps > 0:
+            fault |= ctx.step(args.relax_steps)
+        ob = ctx.observables()
+        row = {"rank": rank, "eta": eta, "seed": rep_seed, "phi": float(ob["phi"]), "mean_speed": float(ob["mean_speed"]),
+               "steps_run": int(ctx.step_index), "lost": int(ob["lost"]), "fault": int(fault)}
+        phase = [row]
+        if dist is not None:
+            phase = [None] * world
+            dist.all_gather_object(phase, row)
+
     if args.no_cpu_baseline:
         if rank == 0:
-            emit(json.dumps({"profiler_run": True, "ms_per_step": ms_per_step, "kernel_ms": prof}))
+            emit(json.dumps({"profiler_run": True, "ms_per_step": ms_per_step, "kernel_ms": prof, "fault": fault,
+                             **({"phase_diagram": phase} if phase else {})}))
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -386,7 +419,8 @@ def main_ours(args, rank, world, local_rank):
                     "step_alg_bytes_per_particle": B_ALG[key],
                     "step_achieved_gbs": B_ALG[key] * Nloc / (ms_per_step * 1e-3) / 1e9,
                     "step_frac": B_ALG[key] * Nloc / (ms_per_step * 1e-3) / 1e9 / peak}
-        cpu_v, cores, kind, sample = run_reference_sample(spec, 3, 1, seconds_budget=20.0)
+        cb = run_port_same_config(spec, 4, 1, seconds_budget=25.0)
+        cb["reference_compiled"] = run_compiled_reference(spec)
         line = {"metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic",
@@ -394,13 +428,16 @@ def main_ours(args, rank, world, local_rank):
                            "mesh_V": int(len(chart["uv"])), "mesh_F": int(len(chart["faces"])),
                            "l2": "per-step working set (%d MB) exceeds the 126 MB L2; no explicit flush" %
                                  int(Nloc * 112 / 1e6 + 32),
-                           "parallelism": ("slab%d: x-slabs of one %d-particle set, NCCL halo + migration exchange per step" %
+                           "parallelism": ("replicas%d: independent contexts, one per GPU, no communication" % world) if replicas else
+                                          ("slab%d: x-slabs of one %d-particle set, NCCL halo + migration exchange per step" %
                                            (world, spec["total"])) if world > 1 else "single",
-                           "fault": fault},
+                           "fault": fault, **({"phase_diagram": phase} if phase else {}),
+                           **({"weak_scaling_note": "per-GPU particle count is fixed, but the chart is refined with the total "
+                               "(2/3/3/4 levels at 1/2/4/8 GPUs) and sigma follows the total particle count, so the per-GPU work "
+                               "is similar, not identical, along the curve"} if args.workload == "c4shard" else {})},
                 "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                 "kernel_ms": prof, "roofline": roof,
-                "cpu_baseline": {"value": cpu_v, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample,
-                                 "port": run_port_sample(spec) if kind == "reference" else None},
+                "cpu_baseline": cb,
                 "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d * world),
                         "d2h_bytes_per_step": int(d2h * world), "steps": e2e_steps}}
         emit(json.dumps(line))
@@ -435,7 +472,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4shard", choices=["c4shard", "c2", "c3"])
+    ap.add_argument("--workload", default="c4shard", choices=["c4shard", "c2", "c3", "c5"])
+    ap.add_argument("--relax-steps", type=int, default=500, help="c5: untimed steps after the timed region, before phi is read")
     ap.add_argument("--particles-per-gpu", type=int, default=0)
     ap.add_argument("--dtype", default=None, choices=[None, "f32", "f64"])
     ap.add_argument("--lift", default="reference", choices=["reference", "barycentric"],
