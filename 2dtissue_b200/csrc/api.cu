@@ -82,6 +82,7 @@ struct EngineBase {
     virtual int observables(double* out) = 0;
     virtual int get_counters(t2d_counters* out) = 0;
     virtual int reset_counters() = 0;
+    virtual int set_tie_log(int on) = 0;
     virtual int set_params(const t2d_params* p) = 0;
     virtual int get_r3d(int N, const double* uv, double* r3d, int* vid, int* face) = 0;
     virtual int tiling(int N, double* uv_old, double* uv, int* heading) = 0;
@@ -142,6 +143,11 @@ template <typename R> class Engine : public EngineBase {
     int observables(double* out) override;
     int get_counters(t2d_counters* out) override;
     int reset_counters() override;
+    int set_tie_log(int on) override
+    {
+        A_.count_ties = on ? 1 : 0;
+        return 0;
+    }
     int set_params(const t2d_params* p) override;
     int get_r3d(int N, const double* uv, double* r3d, int* vid, int* face) override;
     int tiling(int N, double* uv_old, double* uv, int* heading) override;
@@ -293,7 +299,7 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
         const char* e = getenv("T2D_STEP");   // dev knob for A/B measurements: "legacy" = k_step_euclid_fast + the cs array
         use_fast2_ = sizeof(R) == 4 && P_.neigh_mode == T2D_NEIGH_EUCLID && !(e && std::string(e) == "legacy");
         const char* t = getenv("T2D_COUNT_TIES");
-        A_.count_ties = !(t && atoi(t) == 0);
+        A_.count_ties = (t && atoi(t) != 0) ? 1 : 0;   // the tie log is a diagnostic: off unless asked for (t2d_set_tie_log)
     }
     upload_chart();
     if (chart_.table_kind == T2D_TABLE_HOPS_FROM_MESH) {
@@ -1124,11 +1130,13 @@ template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int
     A_.step = (uint64_t)step_index;
     mark();
     if (P_.neigh_mode == T2D_NEIGH_EUCLID) {
-        if (const char* e = getenv("T2D_F2_ABLATE_AFTER")) {   // dev: ablation timing, see step_fast2.cuh
+#ifdef T2D_F2_ABLATE
+        if (const char* e = getenv("T2D_F2_ABLATE_AFTER")) {   // dev builds only: ablation timing, see step_fast2.cuh / tools/gpu_ablate.sh
             static int n_launch = 0;
             const char* m = getenv("T2D_F2_ABLATE_MODE");
             A_.ablate = (++n_launch > atoi(e)) ? (m ? atoi(m) : 0) : 0;
         }
+#endif
         // lean pipeline (fp32 fast path, single context): the step kernel writes records, the sort moves record + aux only;
         // pos / uv / r_dot / colour are rebuilt by materialize() when somebody asks for them
         const bool lean = moving && use_fast2_ && lean_ok_ && !comm_on_;
@@ -1547,6 +1555,7 @@ int t2d_step_host_uv(t2d_ctx* ctx, int32_t N, double* uv, int32_t* heading, int3
 int t2d_observables(t2d_ctx* ctx, double out[T2D_OBS_LEN]) { T2D_TRY(ctx, return ctx->eng->observables(out);) }
 int t2d_get_counters(t2d_ctx* ctx, t2d_counters* out) { T2D_TRY(ctx, return ctx->eng->get_counters(out);) }
 int t2d_reset_counters(t2d_ctx* ctx) { T2D_TRY(ctx, return ctx->eng->reset_counters();) }
+int t2d_set_tie_log(t2d_ctx* ctx, int on) { T2D_TRY(ctx, return ctx->eng->set_tie_log(on);) }
 int64_t t2d_get_step(const t2d_ctx* ctx) { return ctx->eng->step_index; }
 int t2d_set_step(t2d_ctx* ctx, int64_t step)
 {

@@ -33,18 +33,6 @@ constexpr int F2_THREADS = 128;
 #ifndef T2D_F2_UNROLL
 #define T2D_F2_UNROLL 4
 #endif
-#ifndef T2D_F2_REVERSE
-#define T2D_F2_REVERSE 0   // 1: walk the slots from the end (what the scatter wrote last is still in L2)
-#endif
-#ifndef T2D_F2_L2PF
-#define T2D_F2_L2PF 0      // > 0: every grab asks the TMA unit to prefetch the records of the grab this many grabs ahead into L2
-#endif
-#ifndef T2D_F2_PFD
-#define T2D_F2_PFD 0       // > 0: every trip prefetches (L1) the records this many trips ahead; range starts prefetch the next range
-#endif
-#ifndef T2D_F2_LD128
-#define T2D_F2_LD128 0     // 1: candidates are read as LDG.128 {x, y, z, slot} + a predicated LDG.64 {u, v} instead of one LDG.256
-#endif
 constexpr int F2_TRIG_N = 361;   // headings 0..360: what alignment produces (OrientationHelper.cpp:102-116); seam re-entry makes the rest
 constexpr unsigned F2_TIE_ULPS = 8;
 
@@ -109,20 +97,6 @@ __device__ __forceinline__ F2Rec f2_load(const float4* __restrict__ q)
         : "l"(q));
     return r;
 }
-// candidate variant: first half only; (u, v) is fetched by f2_candidate when the pair is in range
-__device__ __forceinline__ F2Rec f2_load_half(const float4* __restrict__ q)
-{
-    F2Rec r;
-    asm("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=r"(r.slot) : "l"(q));
-    r.u = r.v = 0.0f;
-    r.cell = r.heading = 0;
-    return r;
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ double2 f2_lds_trig(uint32_t addr)
 {
     double2 t;
@@ -139,9 +113,8 @@ __device__ __forceinline__ double2 f2_lds_trig(uint32_t addr)
 // sends the thread through the rare global-table path after the group.  TIES: log candidates within F2_TIE_ULPS ulps of a squared cutoff — a
 // neighbour-set or colour difference against the fp64 oracle must be one of these (tests/test_gpu_fastpath.py).
 template <bool TIES>
-__device__ __forceinline__ void f2_candidate(const F2Rec& J, const float4* __restrict__ q, const float px, const float py,
-                                             const float pz, const float2 ui, const F2Consts& k, const uint32_t s_trig, F2Acc& acc,
-                                             unsigned& oobm)
+__device__ __forceinline__ void f2_candidate(const F2Rec& J, const float px, const float py, const float pz, const float2 ui,
+                                             const F2Consts& k, const uint32_t s_trig, F2Acc& acc, unsigned& oobm)
 {
     // hand-scheduled PTX: 25 instructions per candidate, every value defined on every path (nothing for ptxas to spill or
     // to turn into branches); slot 361 = zero entry for "not in range", 362 = zero entry for "heading not in the table"
@@ -158,11 +131,6 @@ __device__ __forceinline__ void f2_candidate(const F2Rec& J, const float4* __res
         "fma.rn.ftz.f32 %7, dy, dy, %7;\n\t"
         "fma.rn.ftz.f32 %7, dz, dz, %7;\n\t"
         "setp.lt.ftz.f32 p, %7, %19;\n\t"
-#if T2D_F2_LD128
-        "mov.f32 ux, 0f00000000;\n\t"
-        "mov.f32 uy, 0f00000000;\n\t"
-        "@p ld.global.nc.v2.f32 {ux, uy}, [%24+16];\n\t"
-#endif
         "setp.neu.ftz.f32 nz, %7, 0f00000000;\n\t"
         "setp.le.and.ftz.f32 c, %7, %20, nz;\n\t"
         "@c add.s32 %4, %4, 1;\n\t"
@@ -176,13 +144,8 @@ __device__ __forceinline__ void f2_candidate(const F2Rec& J, const float4* __res
         "selp.f32 inv, inv, 0f447A0000, nz;\n\t"
         "fma.rn.ftz.f32 g, inv, %21, %22;\n\t"
         "selp.f32 g, g, 0f00000000, p;\n\t"
-#if T2D_F2_LD128
-        "sub.ftz.f32 ux, %17, ux;\n\t"
-        "sub.ftz.f32 uy, %18, uy;\n\t"
-#else
         "sub.ftz.f32 ux, %17, %15;\n\t"
         "sub.ftz.f32 uy, %18, %16;\n\t"
-#endif
         "fma.rn.ftz.f32 %0, g, ux, %0;\n\t"
         "fma.rn.ftz.f32 %1, g, uy, %1;\n\t"
         "add.f64 %2, %2, tc;\n\t"
@@ -190,7 +153,7 @@ __device__ __forceinline__ void f2_candidate(const F2Rec& J, const float4* __res
         "}"
         : "+f"(acc.fx), "+f"(acc.fy), "+d"(acc.mx), "+d"(acc.my), "+r"(acc.color), "+r"(acc.hits), "+r"(oobm), "=f"(d2)
         : "f"(px), "f"(py), "f"(pz), "f"(J.x), "f"(J.y), "f"(J.z), "r"(J.slot), "f"(J.u), "f"(J.v), "f"(ui.x), "f"(ui.y),
-          "f"(k.r2s), "f"(k.r2c), "f"(k.g1), "f"(k.g0), "r"(s_trig), "l"(q));
+          "f"(k.r2s), "f"(k.r2c), "f"(k.g1), "f"(k.g0), "r"(s_trig));
     if (TIES) {
         const unsigned bm1 = __float_as_uint(d2) - 1u;
         if ((bm1 - k.tie_s_lo) <= 2u * F2_TIE_ULPS || (bm1 - k.tie_c_lo) <= 2u * F2_TIE_ULPS) acc.ties++;
@@ -216,15 +179,11 @@ __device__ __forceinline__ void f2_trip(const float4* __restrict__ q, int cnt, c
                                         const float2 ui, const F2Consts& k, const uint32_t s_trig, F2Acc& acc)
 {
     F2Rec J[T2D_F2_UNROLL];
-    const float4* qu[T2D_F2_UNROLL];
 #pragma unroll
-    for (int u = 0; u < T2D_F2_UNROLL; ++u) {
-        qu[u] = (!MASKED || u < cnt) ? q + 2 * u : sent;
-        J[u] = T2D_F2_LD128 ? f2_load_half(qu[u]) : f2_load(qu[u]);
-    }
+    for (int u = 0; u < T2D_F2_UNROLL; ++u) J[u] = f2_load((!MASKED || u < cnt) ? q + 2 * u : sent);
     unsigned oob = 0;
 #pragma unroll
-    for (int u = 0; u < T2D_F2_UNROLL; ++u) f2_candidate<TIES>(J[u], qu[u], px, py, pz, ui, k, s_trig, acc, oob);
+    for (int u = 0; u < T2D_F2_UNROLL; ++u) f2_candidate<TIES>(J[u], px, py, pz, ui, k, s_trig, acc, oob);
     if (__builtin_expect(oob > (unsigned)F2_TRIG_N, 0)) {
 #pragma unroll 1
         for (int u = 0; u < (MASKED ? cnt : T2D_F2_UNROLL); ++u) {
@@ -294,15 +253,8 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
     const int ob = start[M], ol = start[M + 1] - ob;   // overflow bucket: normally empty
     unsigned npairs_w = 0, nties_w = 0, ncut_w = 0, fb_w = 0;
 
-#ifndef T2D_F2_STATIC
-#define T2D_F2_STATIC 0   // 1: rows are dealt round-robin to the resident warps (no queue); 2: queue per 16-row block, rows inside it static
-#endif
     int next = 0;
-#if T2D_F2_STATIC == 1
-    next = blockIdx.x * (F2_THREADS / 32) + (tid >> 5);
-#else
     if (lane == 0) next = atomicAdd(queue, 1);
-#endif
     mbar_wait(&sm.bar, 0);   // the table has landed (every thread observes the barrier itself)
     if (tid < 2) sm.trig[F2_TRIG_N + tid] = make_double2(0.0, 0.0);
     __syncthreads();
@@ -311,21 +263,8 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
     for (;;) {
         const int ticket = __shfl_sync(0xffffffffu, next, 0);
         if (ticket >= ngrabs) break;
-#if T2D_F2_STATIC == 1
-        next += gridDim.x * (F2_THREADS / 32);
-#else
         if (lane == 0) next = atomicAdd(queue, 1);   // in flight while this grab is processed
-#endif
-        const int grab = T2D_F2_REVERSE ? ngrabs - 1 - ticket : ticket;
-#if T2D_F2_L2PF > 0
-        if (lane == 0) {   // ask the TMA unit to bring the records of a later grab into L2 (no register, no scoreboard)
-            const int ahead = T2D_F2_REVERSE ? grab - T2D_F2_L2PF : grab + T2D_F2_L2PF;
-            if (ahead >= 0 && (ahead + 1) * 32 * T2D_F2_GRAB <= nres) {
-                bulk_prefetch_l2(rec + 2 * (size_t)ahead * 32 * T2D_F2_GRAB, 32u * 32u * T2D_F2_GRAB);
-                bulk_prefetch_l2(a.cur.aux + (size_t)ahead * 32 * T2D_F2_GRAB, 16u * 32u * T2D_F2_GRAB);
-            }
-        }
-#endif
+        const int grab = ticket;
 #pragma unroll 1
         for (int sub = 0; sub < T2D_F2_GRAB; ++sub) {
             const int i = (grab * T2D_F2_GRAB + sub) * 32 + lane;
@@ -340,6 +279,10 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
             float2 ui = make_float2(0.0f, 0.0f);
             int nh = 0, own_cell = -1;
             float ox = 0.0f, oy = 0.0f, oz = 0.0f;
+#ifdef T2D_F2_ABLATE
+            for (int rep = 0; rep < (a.ablate == 8 ? 2 : 1); ++rep) {   // dev: second pass = the same work with warm caches
+            if (rep) acc = F2Acc();
+#endif
             if (live) {
                 const F2Rec self = f2_load(rec + 2 * (size_t)i);
                 const float px = self.x, py = self.y, pz = self.z;
@@ -427,20 +370,7 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
                     if (a.ablate == 6) q = rec + 2 * (size_t)max(0, min(i - lane, nres - 4 - len));   // dev: every candidate load hits L1
 #endif
                     int t = 0;
-#if T2D_F2_PFD > 0
-                    if (m + 1 < nr) {   // the first two trips of the NEXT range (the trips below prefetch within this one)
-                        const int kn = sm.rkey[m + 1][tid];
-                        const float4* qn = rec + 2 * (size_t)sm.rbeg[kn & 15][tid];
-                        prefetch_l1(qn);
-                        prefetch_l1(qn + 4);
-                        if ((kn >> 4) > 4) prefetch_l1(qn + 8);
-                    }
-#endif
                     for (; t + T2D_F2_UNROLL <= len; t += T2D_F2_UNROLL, q += 2 * T2D_F2_UNROLL) {
-#if T2D_F2_PFD > 0
-                        prefetch_l1(q + 2 * T2D_F2_UNROLL * T2D_F2_PFD);
-                        prefetch_l1(q + 2 * T2D_F2_UNROLL * T2D_F2_PFD + 2 * T2D_F2_UNROLL - 2);
-#endif
                         f2_trip<TIES, false>(q, T2D_F2_UNROLL, sent, a.trig_d, px, py, pz, ui, k, s_trig, acc);
                     }
                     // the rest of the range as ONE masked trip (the candidates beyond the end read the sentinel record): a
@@ -448,6 +378,9 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
                     if (t < len) f2_trip<TIES, true>(q, len - t, sent, a.trig_d, px, py, pz, ui, k, s_trig, acc);
                 }
             }
+#ifdef T2D_F2_ABLATE
+            }
+#endif
             __syncwarp();   // reconverge: lanes leave the candidate loops at different times, the tail is the same for all
             unsigned npairs = 0, nties = 0;
             if (live) {

@@ -150,7 +150,7 @@ template <typename R> struct StepArgs {
     uint64_t seed, step;
     int mode;
     int write_F;
-    int count_ties = 1;            // fp32 fast path: log candidates within 8 ulps of a cutoff in ties_cutoff
+    int count_ties = 0;            // fp32 fast path: log candidates within 8 ulps of a cutoff in ties_cutoff (t2d_set_tie_log)
     int* work_counter = nullptr;   // [4] dynamic queues: [0] buckets of the table-mode kernel, [1], [2] chunk queues of k_step_fast2
     const float4* rec_sentinel = nullptr;   // one record that is nobody's neighbour: what the masked tail trips of k_step_fast2 read
     int* src = nullptr;            // lean pipeline: sorted slot -> index in the pre-sort arrays (r_dot, colour)

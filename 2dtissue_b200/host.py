@@ -184,6 +184,10 @@ class Context:
     def reset_counters(self):
         self._chk(self.L.t2d_reset_counters(self.h), "t2d_reset_counters")
 
+    def set_tie_log(self, on=True):
+        """fp32 fast path: count candidates within 8 ulps of a squared cutoff in counters()["ties_cutoff"] (off by default)."""
+        self._chk(self.L.t2d_set_tie_log(self.h, 1 if on else 0), "t2d_set_tie_log")
+
     @property
     def step_index(self):
         return self.L.t2d_get_step(self.h)

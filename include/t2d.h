@@ -102,7 +102,8 @@ typedef struct {
     int64_t steps;
     int64_t kernel_launches;   /* kernels of this library launched so far */
     int64_t pairs_in_range;    /* sum_i |{j != i : d_ij < 2 sigma}| */
-    int64_t ties_cutoff;       /* pairs with d_ij == 2 sigma exactly (logged) */
+    int64_t ties_cutoff;       /* fp64: pairs with d_ij == 2 sigma exactly; fp32 fast path: candidates within 8 ulps of a squared
+                                  cutoff, counted only while the tie log is on (t2d_set_tie_log) */
     int64_t ties_trunc;        /* headings whose mean angle is within 1e-9 deg of an integer */
     int64_t wraps;             /* seam re-entries */
     int64_t wrap_cap_hits;
@@ -150,6 +151,11 @@ int t2d_step_host_uv(t2d_ctx* ctx, int32_t N, double* uv, int32_t* heading, int3
 int t2d_observables(t2d_ctx* ctx, double out[T2D_OBS_LEN]);
 int t2d_get_counters(t2d_ctx* ctx, t2d_counters* out);
 int t2d_reset_counters(t2d_ctx* ctx);
+/* fp32 fast path: switch the near-cutoff tie log on (1) or off (0, the default).  The log is how the parity tests tell a
+   legitimate fp32 rounding difference of a neighbour set from an error (every difference against the fp64 oracle must be a
+   logged tie); it runs the same kernel with one extra test per candidate (about +15 % step time), results are identical.
+   T2D_COUNT_TIES=1 in the environment switches it on for every new context. */
+int t2d_set_tie_log(t2d_ctx* ctx, int on);
 /* current step index (the Philox counter's step word); t2d_set_step supports checkpoint/resume */
 int64_t t2d_get_step(const t2d_ctx* ctx);
 int t2d_set_step(t2d_ctx* ctx, int64_t step);

@@ -55,3 +55,39 @@ def test_fp32_long_run_statistics_match_reference_semantics(t2d, chart, oracle):
               (name, g.mean(), g.std(ddof=1) / np.sqrt(nseeds), o.mean(), o.std(ddof=1) / np.sqrt(nseeds),
                abs(g.mean() - o.mean()), 3 * se))
         assert abs(g.mean() - o.mean()) <= 3 * se + 1e-4 * max(1.0, abs(o.mean()))
+
+
+def test_replicas_are_independent(t2d, chart):
+    """Config 5 (noise sweep as independent replicas, bench.py --workload c5): contexts that share a GPU and are stepped in
+    turn do not see each other — each one reproduces the run of the same (eta, seed) alone, bit for bit in fp64 (the exact
+    path sums in ascending id and its noise is keyed by (seed, step, id))."""
+    N = 6000
+    sigma = float(np.sqrt(0.5 * 451.3 / (np.pi * N)))
+    reps = [(0.0, 11), (0.3, 12), (0.9, 13)]
+    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=t2d.NEIGH_EUCLID, precision=t2d.PRECISION_FP64, capacity=N)
+
+    def start(eta, seed):
+        uv, n = t2d.seed_particles(N, seed=seed)
+        ctx = t2d.Context(chart, eta=eta, seed=seed, **kw)
+        ctx.set_particles(uv, n)
+        return ctx
+
+    alone = []
+    for eta, seed in reps:
+        ctx = start(eta, seed)
+        assert ctx.step(12) == 0
+        alone.append((ctx.download(), ctx.observables()))
+        ctx.close()
+    ctxs = [start(eta, seed) for eta, seed in reps]
+    for _ in range(4):           # interleaved: 3 steps of every replica in turn
+        for ctx in ctxs:
+            assert ctx.step(3) == 0
+    for ctx, (ref, obs) in zip(ctxs, alone):
+        out = ctx.download()
+        for k in ("uv", "n", "vid", "r3d", "rdot", "color", "face"):
+            assert np.array_equal(out[k], ref[k]), k
+        assert ctx.observables()["phi"] == obs["phi"]
+        ctx.close()
+    # more noise, less order
+    phis = [o["phi"] for _, o in alone]
+    print("phi(eta):", list(zip([e for e, _ in reps], phis)))
