@@ -86,7 +86,7 @@ def test_replicas_are_independent(t2d, chart):
         out = ctx.download()
         for k in ("uv", "n", "vid", "r3d", "rdot", "color", "face"):
             assert np.array_equal(out[k], ref[k]), k
-        assert ctx.observables()["phi"] == obs["phi"]
+        assert abs(ctx.observables()["phi"] - obs["phi"]) < 1e-12   # the reduction's atomic order is free, the state is not
         ctx.close()
     # more noise, less order
     phis = [o["phi"] for _, o in alone]
