@@ -11,7 +11,9 @@ The directory name starts with a digit, so import it with
 """
 from . import chart  # noqa: F401
 from .chart import load_chart, refine_chart, save_chart  # noqa: F401
+from .table import TableCSR  # noqa: F401
 from .host import (FAULT_LOST, FAULT_NONFINITE, FAULT_WRAP_CAP, NEIGH_EUCLID, NEIGH_TABLE, PRECISION_FP32, PRECISION_FP64, TABLE_DENSE_F32, TABLE_DENSE_F64,  # noqa: F401
                    TABLE_DENSE_U8, TABLE_HOPS_FROM_MESH, TABLE_NONE, Context, LostParticlesError, Particle, System,
                    T2DError, Tissue2D, seed_particles, FAULT_MIGRATION, FAULT_COMM_OVERFLOW, LocalSlabGroup,
-                   comm_unique_id, merge_by_id, partition_by_slab, slab_cuts, slab_of, LIFT_REFERENCE, LIFT_BARYCENTRIC)
+                   comm_unique_id, merge_by_id, partition_by_slab, slab_cuts, slab_of, LIFT_REFERENCE, LIFT_BARYCENTRIC,
+                   TABLE_CSR_F64, TABLE_CSR_F32, TABLE_CSR_U8)

@@ -19,6 +19,11 @@ class Table(C.Structure):
     _fields_ = [("V", C.c_int32), ("kind", C.c_int32), ("data", C.c_void_p)]
 
 
+class TableCSRStruct(C.Structure):   # t2d_table_csr
+    _fields_ = [("nnz", C.c_int64), ("start", C.POINTER(C.c_int32)), ("col", C.POINTER(C.c_int32)), ("val", C.c_void_p),
+                ("radius", C.c_double)]
+
+
 class Params(C.Structure):
     _fields_ = [("v0", C.c_double), ("k", C.c_double), ("sigma", C.c_double), ("step_size", C.c_double),
                 ("eta", C.c_double), ("color_factor", C.c_double), ("seed", C.c_uint64), ("neigh_mode", C.c_int32),

@@ -18,6 +18,8 @@
 
 namespace t2d {
 int launch_hop_table(int V, const int* d_adj_start, const int* d_adj, uint8_t* out_dev, int sm_count, cudaStream_t s);
+int launch_hop_csr(int V, const int* d_adj_start, const int* d_adj, int hops, int* row_len, const int* start, int* col, uint8_t* val,
+                   int sm_count, cudaStream_t s);
 // comm.cu: NCCL transport (libnccl opened at run time)
 struct NcclLink;
 int nccl_unique_id(uint8_t* out, std::string* err);
@@ -118,6 +120,12 @@ struct HostChart {
     int table_kind = T2D_TABLE_NONE;
     int tableV = 0;
     std::vector<uint8_t> table_raw;   // dense table in the caller's stored type
+    // sparse form (T2D_TABLE_CSR_*, or hop counts built on the GPU for large meshes): complete up to csr_radius
+    bool sparse = false;
+    bool sparse_hops = false;         // rows come from build_hop_csr_device and are rebuilt when the radius grows
+    double csr_radius = 0;
+    std::vector<int> csr_start, csr_col;
+    std::vector<double> csr_val;
 
     double table_at(int a, int b) const
     {
@@ -231,6 +239,7 @@ template <typename R> class Engine : public EngineBase {
     bool lean_ok_ = false;                       // the lean pipeline may be used (fp32 Euclid fast path; T2D_LEAN=0 switches it off)
     void scan_buckets();
     void materialize();
+    void build_hop_csr_device(int hops);
     bool use_fast2_ = false;       // fp32 Euclid: k_step_fast2 (step_fast2.cuh) on 32-byte records; T2D_STEP=legacy switches it off
     DevBuf<int> d_csr_start_, d_csr_col_;
     DevBuf<double> d_csr_d_;
@@ -284,6 +293,33 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
         size_t nn = (size_t)table->V * table->V;
         if (table->kind == T2D_TABLE_HOPS_FROM_MESH) {
             // filled after the chart upload (needs the adjacency on the device)
+        } else if (table->kind == T2D_TABLE_CSR_F64 || table->kind == T2D_TABLE_CSR_F32 || table->kind == T2D_TABLE_CSR_U8) {
+            const t2d_table_csr* c = static_cast<const t2d_table_csr*>(table->data);
+            if (!c || !c->start || !c->col || !c->val || c->nnz < 0) throw CudaError{"table CSR is null"};
+            const int V = table->V;
+            if (c->start[0] != 0 || (int64_t)c->start[V] != c->nnz) throw CudaError{"table CSR: start[] does not match nnz"};
+            chart_.sparse = true;
+            chart_.csr_radius = c->radius;
+            chart_.csr_start.assign(c->start, c->start + V + 1);
+            chart_.csr_col.assign(c->col, c->col + c->nnz);
+            chart_.csr_val.resize((size_t)c->nnz);
+            for (int64_t q = 0; q < c->nnz; ++q)
+                chart_.csr_val[(size_t)q] = table->kind == T2D_TABLE_CSR_F64 ? static_cast<const double*>(c->val)[q]
+                                            : table->kind == T2D_TABLE_CSR_F32 ? (double)static_cast<const float*>(c->val)[q]
+                                                                               : (double)static_cast<const uint8_t*>(c->val)[q];
+            for (int v = 0; v < V; ++v) {
+                if (c->start[v + 1] < c->start[v]) throw CudaError{"table CSR: start[] must be non-decreasing"};
+                bool diag = false;
+                for (int q = c->start[v]; q < c->start[v + 1]; ++q) {
+                    const int u = c->col[q];
+                    if (u < 0 || u >= V || (q > c->start[v] && u <= c->col[q - 1])) throw CudaError{"table CSR: columns must ascend inside a row"};
+                    if (u == v) {
+                        diag = true;
+                        if (chart_.csr_val[(size_t)q] != 0.0) throw CudaError{"vertex-distance table must have a zero diagonal"};
+                    }
+                }
+                if (!diag) throw CudaError{"table CSR: every row must hold its diagonal entry"};
+            }
         } else {
             if (!table->data) throw CudaError{"table data is null"};
             size_t es = table->kind == T2D_TABLE_DENSE_F64 ? 8 : (table->kind == T2D_TABLE_DENSE_F32 ? 4 : 1);
@@ -303,8 +339,14 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
     }
     upload_chart();
     if (chart_.table_kind == T2D_TABLE_HOPS_FROM_MESH) {
-        build_hop_table_device(&chart_.table_raw);
-        chart_.table_kind = T2D_TABLE_DENSE_U8;
+        const char* fs = getenv("T2D_HOPS_SPARSE");   // dev/test knob: force the sparse builder on a small mesh
+        if ((double)chart_.V * chart_.V > 1.0e9 || (fs && atoi(fs) != 0)) {
+            chart_.sparse = chart_.sparse_hops = true;   // rows are built (and rebuilt) by apply_params for the radius in force
+            chart_.tableV = chart_.V;
+        } else {
+            build_hop_table_device(&chart_.table_raw);
+            chart_.table_kind = T2D_TABLE_DENSE_U8;
+        }
     }
 
     // particle storage
@@ -519,6 +561,42 @@ template <typename R> void Engine<R>::build_hop_table_device(std::vector<uint8_t
     chart_.tableV = V;
 }
 
+// hop counts up to `hops` as CSR rows, built on the GPU without ever forming the V x V table (hop_table.cu): count pass,
+// host scan of the V row lengths, fill pass
+template <typename R> void Engine<R>::build_hop_csr_device(int hops)
+{
+    const int V = chart_.V;
+    hops = std::max(1, std::min(hops, 254));
+    DevBuf<int> d_len, d_start, d_col;
+    DevBuf<uint8_t> d_val;
+    d_len.alloc((size_t)V + 1);
+    int e = launch_hop_csr(V, d_adj_start_.p, d_adj_.p, hops, d_len.p, nullptr, nullptr, nullptr, sm_count_, stream_);
+    if (e != 0) throw CudaError{std::string("hop-CSR kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
+    std::vector<int> len((size_t)V);
+    CK(cudaMemcpyAsync(len.data(), d_len.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    chart_.csr_start.assign((size_t)V + 1, 0);
+    long long total = 0;
+    for (int v = 0; v < V; ++v) {
+        total += len[(size_t)v];
+        if (total > 2000000000LL) throw CudaError{"hop CSR too large: lower sigma or use a coarser chart"};
+        chart_.csr_start[(size_t)v + 1] = (int)total;
+    }
+    d_start.upload(chart_.csr_start, stream_);
+    d_col.alloc((size_t)total + 1);
+    d_val.alloc((size_t)total + 1);
+    e = launch_hop_csr(V, d_adj_start_.p, d_adj_.p, hops, nullptr, d_start.p, d_col.p, d_val.p, sm_count_, stream_);
+    if (e != 0) throw CudaError{std::string("hop-CSR kernel launch failed: ") + cudaGetErrorString((cudaError_t)e)};
+    launches_ += 2;
+    chart_.csr_col.resize((size_t)total);
+    std::vector<uint8_t> val((size_t)total);
+    CK(cudaMemcpyAsync(chart_.csr_col.data(), d_col.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(val.data(), d_val.p, (size_t)total, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    chart_.csr_val.assign(val.begin(), val.end());
+    chart_.csr_radius = (double)hops;
+}
+
 // thresholded CSR of the table: entries with d < 2σ or d <= color_factor·σ, d = min(D[v][u], D[u][v])
 // (Locomotion.cpp:110 symmetrises by min), kept as doubles — the reference's in-memory precision.
 template <typename R> void Engine<R>::build_csr()
@@ -527,6 +605,22 @@ template <typename R> void Engine<R>::build_csr()
     const double two_sigma = 2 * P_.sigma, color_r = P_.color_factor * P_.sigma;
     std::vector<int> start((size_t)V + 1, 0), col;
     std::vector<double> dv;
+    if (chart_.sparse) {   // the caller's (or the GPU builder's) rows, cut to the radius in force
+        const double rmax = std::max(two_sigma, color_r);
+        if (chart_.sparse_hops && (chart_.csr_start.empty() || rmax > chart_.csr_radius)) build_hop_csr_device((int)std::ceil(rmax));
+        if (rmax > chart_.csr_radius)
+            throw CudaError{"the table CSR is complete up to its radius only: max(2 sigma, color_factor sigma) exceeds it"};
+        for (int v = 0; v < V; ++v) {
+            for (int q = chart_.csr_start[v]; q < chart_.csr_start[v + 1]; ++q) {
+                const double d = chart_.csr_val[(size_t)q];
+                if (d < two_sigma || (d != 0.0 && d <= color_r)) {
+                    col.push_back(chart_.csr_col[(size_t)q]);
+                    dv.push_back(d);
+                }
+            }
+            start[v + 1] = (int)col.size();
+        }
+    } else
     for (int v = 0; v < V; ++v) {
         if (chart_.table_at(v, v) != 0.0) throw CudaError{"vertex-distance table must have a zero diagonal"};
         for (int u = 0; u < V; ++u) {

@@ -1321,6 +1321,103 @@ template <typename R, bool EXACT, int THREADS> __global__ void __launch_bounds__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K3 for the table criterion, fp32 fast path: one WARP per bucket, no shared memory, no barriers.
+// All particles of bucket v share one neighbour set (see above), so the lanes of the warp are the bucket's particles
+// (32 at a time) and the neighbour list is walked in lockstep: every load of a neighbour's (uv, heading, id) is one
+// uniform request, every lane adds the same unit vector and its own force term.  The fast path sums in staging
+// order anyway (the CTA kernel above sorts by id only on the exact path), so the arithmetic is that kernel's
+// walk_tile(sorted = false) — but a bucket of 13 particles (config 3 on the refined chart: 75 k buckets) no longer
+// occupies a 256-thread CTA and a dozen barriers: measured 2.3 ms -> see DESIGN.md for 1 M particles.
+// ---------------------------------------------------------------------------------------------------
+template <typename R> __global__ void __launch_bounds__(128) k_neigh_table_warp(StepArgs<R> a)
+{
+    const int lane = threadIdx.x & 31;
+    BlockCounters bc;
+    int next = 0;
+    if (lane == 0) next = atomicAdd(a.work_counter, 1);
+    for (;;) {
+        const int v = __shfl_sync(0xffffffffu, next, 0);
+        if (v >= a.csr.V) break;
+        if (lane == 0) next = atomicAdd(a.work_counter, 1);
+        const int pb = a.start[v], pe = a.start[v + 1];
+        if (pb == pe) continue;
+        const int rb = a.csr.start[v], re = a.csr.start[v + 1];
+        int col = 0, kr = 0;
+        for (int e = rb + lane; e < re; e += 32) {
+            const int u = a.csr.col[e];
+            const double d = a.csr.d[e];
+            const int cu = a.start[u + 1] - a.start[u];
+            if (d != 0.0 && d <= a.color_r_d) col += cu;
+            if (d < a.two_sigma_d) kr += cu;
+            if (d == a.two_sigma_d) bc.ties_cut += (unsigned long long)cu * (unsigned long long)(pe - pb);
+        }
+        const int color_bucket = __reduce_add_sync(0xffffffffu, col);
+        const int krange = __reduce_add_sync(0xffffffffu, kr);
+        if (lane == 0 && (unsigned long long)krange > bc.max_row) bc.max_row = krange;
+        for (int p0 = pb; p0 < pe; p0 += 32) {
+            const int slot = p0 + lane;
+            const bool act = slot < pe;
+            Real2<R> ui = {R(0), R(0)};
+            int heading = 0;
+            uint32_t my_id = 0xffffffffu;
+            if (act) {
+                ui = a.cur.uv[slot];
+                heading = (int)a.cur.pos[slot].w;
+                my_id = (uint32_t)a.cur.aux[slot].z;
+            }
+            R fx = 0, fy = 0;
+            double mx = 0, my = 0;
+            for (int e = rb; e < re; ++e) {
+                const double d = a.csr.d[e];
+                if (!(d < a.two_sigma_d)) continue;
+                const int u = a.csr.col[e];
+                const int sb = a.start[u], se = a.start[u + 1];
+                R dd = (R)d;
+                if (dd == R(0)) dd += R(0.001);   // ForceHelper.cpp:59-62
+                const R Fij = pair_fij<R>(a.k, a.two_sigma, dd);
+                for (int q0 = sb; q0 < se; q0 += 32) {   // 32 neighbours per round: one coalesced load each, then broadcast
+                    const int q = q0 + lane;
+                    Real2<R> uq = {R(0), R(0)};
+                    double2 tq = make_double2(0.0, 0.0);
+                    uint32_t idq = 0;
+                    if (q < se) {
+                        uq = a.cur.uv[q];
+                        tq = trig_lookup(a.trig_d, (int)a.cur.pos[q].w, bc.trig_fb);
+                        idq = (uint32_t)a.cur.aux[q].z;
+                    }
+                    const int cnt = min(32, se - q0);
+                    for (int t = 0; t < cnt; ++t) {
+                        const R ujx = __shfl_sync(0xffffffffu, uq.x, t), ujy = __shfl_sync(0xffffffffu, uq.y, t);
+                        const double c = __shfl_sync(0xffffffffu, tq.x, t), sn = __shfl_sync(0xffffffffu, tq.y, t);
+                        const uint32_t idj = __shfl_sync(0xffffffffu, idq, t);
+                        mx += c;
+                        my += sn;
+                        if (idj != my_id) {
+                            fx += Fij * ((ui.x - ujx) / dd);
+                            fy += Fij * ((ui.y - ujy) / dd);
+                        }
+                    }
+                }
+            }
+            if (act) {
+                bc.pairs += (unsigned long long)(krange - 1);
+                const Real2<R> rd = velocity_from_force<R>(a, heading, fx, fy, bc);
+                a.cur.rdot[slot] = rd;
+                a.cur.color[slot] = color_bucket;   // the table's diagonal is 0 (checked at upload): self never counts
+                Real2<R> un = {ui.x + rd.x * a.step_size, ui.y + rd.y * a.step_size};
+                a.uv_new[slot] = un;
+                if (a.write_F) {
+                    Real2<R> Fv = {fx, fy};
+                    a.F[slot] = Fv;
+                }
+                a.new_heading[slot] = heading_from_sum<R>(a, mx, my, my_id, bc);
+            }
+        }
+    }
+    flush_counters(bc, a.counters);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // slab mode.  After the step kernel wrote the new state: classify every owned particle by
 // its new 3-D x — stays / migrates to slab-1 or slab+1 — pack migrants (full state) and halo copies (what the
 // neighbour search reads) into the two fixed-capacity messages, and emit key + rank + histogram for what
@@ -1607,6 +1704,13 @@ template <typename R> size_t Launch<R>::comm_message_bytes(int mig_cap, int ghos
 template <typename R> void Launch<R>::neigh_table(const StepArgs<R>& a, cudaStream_t s, int sm_count)
 {
     if (a.N <= 0) return;
+    if constexpr (sizeof(R) == 4) {   // fast path: warp per bucket (the exact path needs the CTA kernel's sort by id)
+        cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
+        int grid = sm_count * 8;
+        if (grid > div_up(a.csr.V, 4)) grid = div_up(a.csr.V, 4);
+        k_neigh_table_warp<R><<<grid, 128, 0, s>>>(a);
+        return;
+    }
     constexpr int THREADS = 256;
     auto kern = k_neigh_table<R, sizeof(R) == 8, THREADS>;
     size_t smem = TableSmem<R>::BYTES;

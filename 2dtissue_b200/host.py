@@ -7,9 +7,11 @@ from typing import List
 import numpy as np
 
 from . import _lib
-from ._lib import Counters, Mesh, Params, Table
+from ._lib import Counters, Mesh, Params, Table, TableCSRStruct
+from .table import TableCSR
 
 TABLE_NONE, TABLE_DENSE_F64, TABLE_DENSE_F32, TABLE_DENSE_U8, TABLE_HOPS_FROM_MESH = 0, 1, 2, 3, 4
+TABLE_CSR_F64, TABLE_CSR_F32, TABLE_CSR_U8 = 5, 6, 7
 NEIGH_TABLE, NEIGH_EUCLID = 0, 1
 PRECISION_FP64, PRECISION_FP32 = 0, 1
 FAULT_LOST, FAULT_NONFINITE, FAULT_WRAP_CAP, FAULT_MIGRATION, FAULT_COMM_OVERFLOW = 1, 2, 4, 8, 16
@@ -50,6 +52,11 @@ class Context:
         self._table = None
         if table_kind == TABLE_HOPS_FROM_MESH:
             tab = Table(self.V, TABLE_HOPS_FROM_MESH, None)
+        elif isinstance(table, TableCSR):   # thresholded rows (include/t2d.h t2d_table_csr)
+            kind = {np.dtype(np.float64): TABLE_CSR_F64, np.dtype(np.float32): TABLE_CSR_F32, np.dtype(np.uint8): TABLE_CSR_U8}[table.val.dtype]
+            self._table = table
+            self._csr = TableCSRStruct(table.nnz, _i(table.start), _i(table.col), table.val.ctypes.data_as(C.c_void_p), table.radius)
+            tab = Table(table.V, kind, C.cast(C.pointer(self._csr), C.c_void_p))
         elif table is not None:
             t = np.ascontiguousarray(table)
             kind = {np.dtype(np.float64): TABLE_DENSE_F64, np.dtype(np.float32): TABLE_DENSE_F32,

@@ -116,8 +116,15 @@ def workload_spec(args, world):
         return dict(name="c2: 10k particles, ellipsoid_x4 chart, Euclidean cutoff", per_gpu=10_000, total=10_000 * world,
                     mode="euclid", refine=0, dtype=args.dtype or "f32")
     if w == "c3":
-        return dict(name="c3: 1M particles, ellipsoid_x4 chart, hop-count vertex-distance table", per_gpu=1_000_000,
-                    total=1_000_000 * world, mode="table", refine=0, dtype=args.dtype or "f32")
+        # the stock 4725-vertex chart puts 211 particles on every vertex (table distance 0 -> the reference's d := 0.001 rule ->
+        # speeds of 1e2-1e5 chart widths): the reference itself would throw.  On the chart refined 2 levels (74.9 k vertices,
+        # ~13 particles per vertex) the run is stable; its table only exists as thresholded CSR rows built on the GPU
+        # k = 0.01: particles that share a nearest vertex are at table distance 0, which the reference turns into d = 0.001
+        # (ForceHelper.cpp:59-62), i.e. a force of 1000 k |u_i - u_j| per pair; with k = 1 the mean speed is 85 chart widths per
+        # unit time (8 % of the chart per step) and a run is one rare close pair away from losing particles
+        return dict(name="c3: 1M particles, ellipsoid chart refined 2 levels (74.9k vertices), hop-count vertex-distance table as "
+                         "thresholded CSR rows built on the GPU, k = 0.01", per_gpu=1_000_000, total=1_000_000 * world, mode="table",
+                    refine=2, dtype=args.dtype or "f32", k=0.01)
     if w == "c5":
         per = args.particles_per_gpu or 1_000_000
         return dict(name="c5: noise sweep, %d independent replica(s) of %d particles, one per GPU, eta = k/(R-1) (R > 1) or 0.25, "
@@ -149,7 +156,11 @@ def run_port_same_config(spec, steps, warmup, seconds_budget=60.0):
     from oracle import oraclebind
     mode = 1 if spec["mode"] == "euclid" else 0
     N = spec["per_gpu"] if spec.get("replicas") else spec["total"]
-    chart = load_chart(t2d, spec["refine"])
+    same = True
+    refine = spec["refine"]
+    if mode == 0 and refine > 0:   # the oracle holds the reference's dense V x V table: not on a 75 k-vertex chart (5.6 GB as uint8)
+        refine, same, N = 0, False, min(N, 50_000)
+    chart = load_chart(t2d, refine)
     orc = oraclebind.Oracle(chart)
     if mode == 0:
         orc.set_table(orc.build_hop_table())
@@ -162,25 +173,26 @@ def run_port_same_config(spec, steps, warmup, seconds_budget=60.0):
     t_start = time.perf_counter()
     done_w = 0
     for _ in range(max(1, warmup)):   # untimed; cut short if one step already eats a third of the budget
-        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, eta=eta, seed=1234, mode=mode, threads=cores,
-                      step_index=done_w)
+        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, spec.get("k", 1.0), sigma, 0.001, eta=eta, seed=1234, mode=mode,
+                      threads=cores, step_index=done_w)
         done_w += 1
         if time.perf_counter() - t_start > seconds_budget / 3:
             break
     t0 = time.perf_counter()
     done = 0
     for _ in range(max(1, steps)):
-        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, 1.0, sigma, 0.001, eta=eta, seed=1234, mode=mode, threads=cores,
-                      step_index=done_w + done)
+        st = orc.step(st["uv"], st["n"], st["vid"], st["r3d"], 0.1, spec.get("k", 1.0), sigma, 0.001, eta=eta, seed=1234, mode=mode,
+                      threads=cores, step_index=done_w + done)
         done += 1
         if time.perf_counter() - t_start > seconds_budget:
             break
     dt = time.perf_counter() - t0
     return {"value": N * done / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-            "sample": ("same configuration as the GPU arm (%s): %d particles, sigma %.6g, %d-face chart, seeded state; O(N k) cell-list "
+            "sample": (("same configuration as the GPU arm" if same else "NOT the GPU arm's chart: dense-table oracle on the unrefined chart") +
+                       " (%s): %d particles, sigma %.6g, %d-face chart, seeded state; O(N k) cell-list "
                        "restatement of the reference's step (oracle/t2d_oracle.c, OpenMP, %d threads), %d warm-up + %d timed steps"
                        % (spec["mode"], N, sigma, len(chart["faces"]), cores, done_w, done)),
-            "same_config": True, "fault": int(st["fault"])}
+            "same_config": same, "fault": int(st["fault"])}
 
 
 def run_compiled_reference(spec, seconds_budget=8.0):
@@ -264,7 +276,7 @@ def main_ours(args, rank, world, local_rank):
     if slabs and mode != t2d.NEIGH_EUCLID:
         raise SystemExit("multi-GPU slabs support the Euclidean criterion (workloads c4shard / c2)")
     cap = int(Nloc * 1.25) + 65536 if slabs else Nloc      # room for halo copies and migration imbalance
-    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=cap, device=local_rank,
+    kw = dict(v0=0.1, k=spec.get("k", 1.0), sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=cap, device=local_rank,
               lift_mode=t2d.LIFT_BARYCENTRIC if args.lift == "barycentric" else t2d.LIFT_REFERENCE)
     if args.lift == "barycentric":
         spec["name"] += ", barycentric lift (extension, not the reference's semantics)"

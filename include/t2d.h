@@ -47,9 +47,25 @@ enum {
     T2D_TABLE_DENSE_F64 = 1,      /* double[V][V], what the reference holds in memory */
     T2D_TABLE_DENSE_F32 = 2,      /* float[V][V]; entries are widened to double before every comparison */
     T2D_TABLE_DENSE_U8 = 3,       /* uint8[V][V] hop counts (255 = farther than 254 hops) */
-    T2D_TABLE_HOPS_FROM_MESH = 4  /* build the hop-count table on the GPU from the mesh's edge graph
-                                     (replaces DijkstraDistanceHelper.cpp:27-111); data is ignored */
+    T2D_TABLE_HOPS_FROM_MESH = 4, /* build the hop-count table on the GPU from the mesh's edge graph
+                                     (replaces DijkstraDistanceHelper.cpp:27-111); data is ignored.  Meshes whose dense table
+                                     would exceed 1 GB get the thresholded CSR built directly (no V x V array anywhere) */
+    T2D_TABLE_CSR_F64 = 5,        /* thresholded table in CSR form, data -> t2d_table_csr, values double */
+    T2D_TABLE_CSR_F32 = 6,        /* the same with float values (widened to double before every comparison) */
+    T2D_TABLE_CSR_U8 = 7          /* the same with uint8 hop counts */
 };
+/* A vertex-distance table that only lists the pairs that can ever interact: row v = the vertices u with
+ * D(v, u) <= radius, ascending u, the diagonal included, already symmetrised by min(D(v,u), D(u,v)) as Locomotion.cpp:110
+ * does.  `radius` is the distance up to which the rows are complete; t2d_create / t2d_set_params refuse an interaction
+ * radius max(2 sigma, color_factor sigma) beyond it.  What the dense kinds cost in memory (V = 75 k: 45 GB as double, the
+ * reference's own format) this kind does not: it is what stage 2 actually reads. */
+typedef struct {
+    int64_t nnz;
+    const int32_t* start; /* [V + 1] */
+    const int32_t* col;   /* [nnz] ascending inside a row */
+    const void* val;      /* [nnz] double / float / uint8 by kind */
+    double radius;
+} t2d_table_csr;
 typedef struct {
     int32_t V;
     int32_t kind;
