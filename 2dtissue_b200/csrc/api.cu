@@ -85,6 +85,7 @@ struct EngineBase {
     virtual int get_counters(t2d_counters* out) = 0;
     virtual int reset_counters() = 0;
     virtual int set_tie_log(int on) = 0;
+    virtual int seed_particles(int N, uint64_t seed, int mode, uint32_t first_id) = 0;
     virtual int set_params(const t2d_params* p) = 0;
     virtual int get_r3d(int N, const double* uv, double* r3d, int* vid, int* face) = 0;
     virtual int tiling(int N, double* uv_old, double* uv, int* heading) = 0;
@@ -151,6 +152,7 @@ template <typename R> class Engine : public EngineBase {
     int observables(double* out) override;
     int get_counters(t2d_counters* out) override;
     int reset_counters() override;
+    int seed_particles(int N, uint64_t seed, int mode, uint32_t first_id) override;
     int set_tie_log(int on) override
     {
         A_.count_ties = on ? 1 : 0;
@@ -941,6 +943,25 @@ int Engine<R>::set_state(int N, const double* uv, const int* heading, const int*
     return 0;
 }
 
+// device-side seeding (io_kernels.cuh k_seed) + the initial projection and sort: no host array is involved
+template <typename R> int Engine<R>::seed_particles(int N, uint64_t seed, int mode, uint32_t first_id)
+{
+    if (N < 0 || N > capacity_) throw CudaError{"particle count exceeds the context's capacity"};
+    if (comm_on_) throw CudaError{"t2d_seed_particles: seed before t2d_comm_init, or upload the slab with t2d_set_state"};
+    if (mode != 0 && mode != 1) throw CudaError{"t2d_seed_particles: mode must be 0 (uniform in the chart) or 1 (face centres)"};
+    CK(cudaSetDevice(device_));
+    lean_ = false;
+    this->N = N;
+    A_.N = N;
+    IoLaunch<R>::seed(N, seed, mode, first_id, chart_.F, A_.mesh.tri, A_.cur, stream_);
+    Launch<R>::project_only(A_, stream_);
+    launches_ += 2;
+    resort(false);
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // slab mode: stable compaction of the owned particles (halo copies are skipped): offsets in d_coff_
 template <typename R> int Engine<R>::compact_owned()
 {
@@ -1650,6 +1671,10 @@ int t2d_observables(t2d_ctx* ctx, double out[T2D_OBS_LEN]) { T2D_TRY(ctx, return
 int t2d_get_counters(t2d_ctx* ctx, t2d_counters* out) { T2D_TRY(ctx, return ctx->eng->get_counters(out);) }
 int t2d_reset_counters(t2d_ctx* ctx) { T2D_TRY(ctx, return ctx->eng->reset_counters();) }
 int t2d_set_tie_log(t2d_ctx* ctx, int on) { T2D_TRY(ctx, return ctx->eng->set_tie_log(on);) }
+int t2d_seed_particles(t2d_ctx* ctx, int32_t N, uint64_t seed, int32_t mode, uint32_t first_id)
+{
+    T2D_TRY(ctx, return ctx->eng->seed_particles(N, seed, mode, first_id);)
+}
 int64_t t2d_get_step(const t2d_ctx* ctx) { return ctx->eng->step_index; }
 int t2d_set_step(t2d_ctx* ctx, int64_t step)
 {

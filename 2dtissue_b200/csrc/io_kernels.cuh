@@ -46,6 +46,40 @@ __global__ void __launch_bounds__(256) k_ingest(int N, HostViewIn in, ParticleAr
     p.color[i] = 0;
 }
 
+// Device-side seeding (replaces CellHelper::init_particle_position, CellHelper.cpp:43-67, whose
+// std::random_device / mt19937 stream is neither reproducible nor parallel): particle i draws from the Philox stream
+// (seed, draw k, id).  mode 0 = the synthetic inputs of §8d: u, v ~ U(0, 1), heading ~ U{0..359}; mode 1 = the reference's
+// scheme: the gravity centre of a random face (drawn with replacement — the reference erases drawn faces from a list it
+// searches linearly, which only works while N << F) and a random heading.
+template <typename R>
+__global__ void __launch_bounds__(256) k_seed(int N, uint64_t seed, int mode, uint32_t first_id, int F, const TriUV<R>* __restrict__ tri,
+                                              ParticleArrays<R> p)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t id = first_id + (uint32_t)i;
+    Real2<R> u;
+    if (mode == 1) {
+        int f = (int)(philox_uniform(seed, 0, id) * (double)F);
+        f = f < 0 ? 0 : (f > F - 1 ? F - 1 : f);
+        const TriUV<R> t = tri[f];
+        u.x = (t.ax + t.bx + t.cx) / R(3);   // get_face_gravity_center_coord
+        u.y = (t.ay + t.by + t.cy) / R(3);
+    } else {
+        u.x = (R)philox_uniform(seed, 0, id);
+        u.y = (R)philox_uniform(seed, 1, id);
+    }
+    int h = (int)(philox_uniform(seed, 2, id) * 360.0);
+    h = h > 359 ? 359 : h;
+    p.uv[i] = u;
+    Pos3<R> X = {R(0), R(0), R(0), (R)h};
+    p.pos[i] = X;
+    p.aux[i] = make_int4(0, -1, (int)id, i);
+    Real2<R> z = {R(0), R(0)};
+    p.rdot[i] = z;
+    p.color[i] = 0;
+}
+
 // slot s holds the particle that sits at index aux[s].w of the caller's arrays.  Slab mode (offsets != null): halo
 // copies are skipped and owned particles are written in slot order at their compaction offset.
 template <typename R>
@@ -123,6 +157,8 @@ template <typename R> struct IoLaunch {
     static void ingest(int N, const HostViewIn& in, const ParticleArrays<R>& p, cudaStream_t s);
     static void egest(int resident, int N, const int* offsets, const ParticleArrays<R>& p, const Real2<R>* F,
                       const int* new_heading, const HostViewOut& out, cudaStream_t s);
+    static void seed(int N, uint64_t seed, int mode, uint32_t first_id, int F, const TriUV<R>* tri, const ParticleArrays<R>& p,
+                     cudaStream_t s);
     static void owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s);
     static void in2(int N, const double* src, Real2<R>* dst, cudaStream_t s);
     static void out2(int N, const Real2<R>* src, double* dst, cudaStream_t s);
@@ -140,6 +176,12 @@ void IoLaunch<R>::egest(int resident, int N, const int* offsets, const ParticleA
                         const int* new_heading, const HostViewOut& out, cudaStream_t s)
 {
     if (resident > 0) k_egest<R><<<(resident + 255) / 256, 256, 0, s>>>(resident, N, offsets, p, F, new_heading, out);
+}
+template <typename R>
+void IoLaunch<R>::seed(int N, uint64_t seed, int mode, uint32_t first_id, int F, const TriUV<R>* tri, const ParticleArrays<R>& p,
+                       cudaStream_t s)
+{
+    if (N > 0) k_seed<R><<<(N + 255) / 256, 256, 0, s>>>(N, seed, mode, first_id, F, tri, p);
 }
 template <typename R> void IoLaunch<R>::owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s)
 {

@@ -105,6 +105,11 @@ class Context:
             idp = ids.ctypes.data_as(_up)
         self._chk(self.L.t2d_set_particles(self.h, heading.size, _d(uv), _i(heading), idp), "t2d_set_particles")
 
+    def seed_on_device(self, N, seed=1234, mode=0, first_id=0):
+        """t2d_seed_particles: Philox-seeded particles + initial projection entirely on the GPU (mode 0: uniform in the chart,
+        mode 1: face centres like CellHelper::init_particle_position)."""
+        self._chk(self.L.t2d_seed_particles(self.h, int(N), int(seed), int(mode), int(first_id)), "t2d_seed_particles")
+
     def set_state(self, uv, heading, vid, r3d, ids=None):
         uv = np.ascontiguousarray(uv, dtype=np.float64)
         heading = np.ascontiguousarray(heading, dtype=np.int32)

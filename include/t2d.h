@@ -143,6 +143,11 @@ int t2d_version(void);
 /* replaces _2DTissue::start after init_particle_position (2DTissue.cpp:117-134): uploads r_UV and n and
  * runs the initial projection (CellHelper::get_r3d) to obtain r_3D / vertices_3D_active.  ids may be NULL. */
 int t2d_set_particles(t2d_ctx* ctx, int32_t N, const double* uv, const int32_t* heading, const uint32_t* ids);
+/* Device-side seeding + initial projection, no host arrays (replaces CellHelper::init_particle_position, CellHelper.cpp:43-67).
+ * Particle i gets global id first_id + i and draws from the Philox4x32-10 stream keyed by (seed, draw, id):
+ * mode 0: u, v ~ U(0, 1), heading ~ U{0..359} (the synthetic inputs of SURVEY.md 8d);
+ * mode 1: the reference's scheme — the gravity centre of a random face and a random heading. */
+int t2d_seed_particles(t2d_ctx* ctx, int32_t N, uint64_t seed, int32_t mode, uint32_t first_id);
 /* full state injection (uv, heading, vid, r3d as a previous step left them); used by t2d_step_host */
 int t2d_set_state(t2d_ctx* ctx, int32_t N, const double* uv, const int32_t* heading, const int32_t* vid,
                   const double* r3d, const uint32_t* ids);

@@ -513,3 +513,33 @@ def test_coincident_in_3d_but_not_in_uv(t2d, chart, oracle):
             sc = np.maximum(np.concatenate([speed, speed]), 1.0)
             assert np.max(np.abs(g["rdot"] - o["rdot"]) / sc) <= tol
         ctx.close()
+
+
+def test_device_side_seeding(t2d, chart):
+    """Row f3: t2d_seed_particles — Philox-seeded start state + projection on the device, no host arrays.  Reproducible from
+    the seed, uniform in the chart (mode 0) or on face centres like CellHelper::init_particle_position (mode 1)."""
+    N = 200_000
+    ctx = t2d.Context(chart, neigh_mode=t2d.NEIGH_EUCLID, precision=t2d.PRECISION_FP64, sigma=0.01, capacity=N)
+    ctx.seed_on_device(N, seed=5)
+    a = ctx.download()
+    ctx.seed_on_device(N, seed=5)
+    b = ctx.download()
+    ctx.seed_on_device(N, seed=6)
+    c = ctx.download()
+    for k in ("uv", "n", "vid", "r3d", "face"):
+        assert np.array_equal(a[k], b[k]), k
+    assert not np.array_equal(a["uv"], c["uv"])
+    u, v = a["uv"][:N], a["uv"][N:]
+    assert u.min() >= 0 and u.max() < 1 and v.min() >= 0 and v.max() < 1
+    assert abs(u.mean() - 0.5) < 5e-3 and abs(v.mean() - 0.5) < 5e-3 and abs(np.corrcoef(u, v)[0, 1]) < 0.01
+    assert a["n"].min() == 0 and a["n"].max() == 359 and abs(a["n"].mean() - 179.5) < 1.5
+    hist = np.histogram(u, bins=20, range=(0, 1))[0]
+    assert hist.min() > 0.9 * N / 20 and hist.max() < 1.1 * N / 20
+    assert ctx.step(2) == 0                                  # a valid start state for the step
+    ctx.seed_on_device(5000, seed=9, mode=1)                 # face centres
+    s = ctx.download()
+    uvc = np.asarray(chart["uv"])[np.asarray(chart["faces"])].mean(axis=1)     # [F][2]
+    f = s["face"]
+    assert np.allclose(np.stack([s["uv"][:5000], s["uv"][5000:]], axis=1), uvc[f], atol=1e-12)
+    assert len(np.unique(f)) > 0.3 * min(5000, len(uvc))
+    ctx.close()
