@@ -8,8 +8,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
+#include <functional>
 #include <memory>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -241,6 +246,11 @@ template <typename R> class Engine : public EngineBase {
     bool lean_ok_ = false;                       // the lean pipeline may be used (fp32 Euclid fast path; T2D_LEAN=0 switches it off)
     void scan_buckets();
     void materialize();
+    // host-buffer path of fp32 contexts: float staging + widening on host threads, chunked so that it overlaps the transfers
+    float* h32_ = nullptr;          // pinned: [5N] in (uv, r3d) followed by [7N] out (uv, r3d, rdot)
+    size_t h32_cap_ = 0;            // particles the pinned staging holds
+    cudaEvent_t ev_chunk_[16] = {};
+    int step_host32(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, bool reproject);
     void build_hop_csr_device(int hops);
     bool use_fast2_ = false;       // fp32 Euclid: k_step_fast2 (step_fast2.cuh) on 32-byte records; T2D_STEP=legacy switches it off
     DevBuf<int> d_csr_start_, d_csr_col_;
@@ -433,6 +443,9 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
 
 template <typename R> Engine<R>::~Engine()
 {
+    if (h32_) cudaFreeHost(h32_);
+    for (auto& e : ev_chunk_)
+        if (e) cudaEventDestroy(e);
     closing_ = true;
     comm_destroy();
     if (ev0_) cudaEventDestroy(ev0_);
@@ -1357,12 +1370,135 @@ template <typename R>
 int Engine<R>::step_host(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, bool reproject)
 {
     if (comm_on_) throw CudaError{"t2d_step_host is not available in slab mode"};
+    {
+        const char* e = getenv("T2D_HOST32");   // dev knob: 0 = the plain path (doubles over PCIe, conversion on the device)
+        if (sizeof(R) == 4 && N >= 4096 && !(e && atoi(e) == 0)) return step_host32(N, uv, heading, vid, r3d, rdot, color, reproject);
+    }
     if (reproject)
         set_state(N, uv, heading, nullptr, nullptr, nullptr, true);
     else
         set_state(N, uv, heading, vid, r3d, nullptr, false);
     int fault = step(1);
     download(uv, heading, vid, r3d, rdot, color, nullptr);
+    return fault;
+}
+
+// run fn(t) for t = 0 .. nt-1 on host threads (OpenMP keeps its pool alive between calls; num_threads overrides the
+// OMP_NUM_THREADS=1 that torchrun exports)
+static void host_parallel(int nt, const std::function<void(int)>& fn)
+{
+#pragma omp parallel num_threads(nt)
+    {
+#pragma omp for schedule(static, 1)
+        for (int t = 0; t < nt; ++t) fn(t);
+    }
+}
+
+// t2d_step_host / t2d_step_host_uv for fp32 contexts.  The fast path computes in float, so doubles on the PCIe bus are
+// padding: 40 + 136 MB per step at 2 M particles as doubles, 24 + 80 MB as floats.  The caller's arrays stay doubles in the
+// reference's layouts; they are narrowed (inputs) and widened (outputs — exact) by host threads in chunks, each chunk while
+// the next one is on the bus.  One stream, no synchronisation until the first output chunk is needed.
+template <typename R>
+int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3d, double* rdot, int* color, bool reproject)
+{
+    if (N < 0 || N > capacity_) throw CudaError{"particle count exceeds the context's capacity"};
+    if (!uv || !heading || !vid || !r3d || !rdot || !color) throw CudaError{"t2d_step_host: all six arrays are required"};
+    CK(cudaSetDevice(device_));
+    const size_t n = (size_t)N;
+    if (h32_cap_ < n) {
+        if (h32_) cudaFreeHost(h32_);
+        h32_ = nullptr;
+        CK(cudaHostAlloc((void**)&h32_, sizeof(float) * 12 * (size_t)capacity_, cudaHostAllocDefault));
+        h32_cap_ = (size_t)capacity_;
+        for (auto& e : ev_chunk_)
+            if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    int K = 4;                                            // chunks per array (<= 16)
+    if (const char* e = getenv("T2D_HOST32_T")) nt = std::max(1, std::min(64, atoi(e)));
+    if (const char* e = getenv("T2D_HOST32_K")) K = std::max(1, std::min(16, atoi(e)));
+    const size_t cs = ((n + K - 1) / K + 63) & ~(size_t)63;
+    float* hin = h32_;                                    // [2n] uv, then [3n] r3d
+    float* hout = h32_ + 5 * (size_t)capacity_;           // [2n] uv, [3n] r3d, [2n] rdot
+    float* din = (float*)d_stage_in_.p;                   // device staging, same layout as hin + ints behind
+    int* din_i = (int*)(din + 5 * n);                     // heading [n], vid [n]
+    float* dout = (float*)d_stage_out_.p;                 // [7n] floats, then heading, vid, color
+    int* dout_i = (int*)(dout + 7 * n);
+    const int ncol_in = reproject ? 2 : 5;
+    // ---- inputs: narrow a chunk on the host threads, put it on the bus, narrow the next one meanwhile ----
+    for (int c = 0; c < K; ++c) {
+        const size_t a = std::min(n, (size_t)c * cs), b = std::min(n, a + cs);
+        if (a == b) break;
+        host_parallel(nt, [&](int t) {
+            const size_t len = b - a, ta = a + len * t / nt, tb = a + len * (t + 1) / nt;
+            for (int col = 0; col < ncol_in; ++col) {
+                const double* src = col < 2 ? uv + col * n : r3d + (col - 2) * n;
+                float* dst = hin + col * n;
+                for (size_t i = ta; i < tb; ++i) dst[i] = (float)src[i];
+            }
+        });
+        for (int col = 0; col < ncol_in; ++col)
+            CK(cudaMemcpyAsync(din + col * n + a, hin + col * n + a, sizeof(float) * (b - a), cudaMemcpyHostToDevice, stream_));
+    }
+    CK(cudaMemcpyAsync(din_i, heading, sizeof(int) * n, cudaMemcpyHostToDevice, stream_));
+    if (!reproject) CK(cudaMemcpyAsync(din_i + n, vid, sizeof(int) * n, cudaMemcpyHostToDevice, stream_));
+    lean_ = false;
+    this->N = N;
+    A_.N = N;
+    HostViewIn32 in{din, din_i, reproject ? nullptr : din_i + n, reproject ? nullptr : din + 2 * n};
+    IoLaunch<R>::ingest32(N, in, A_.cur, stream_);
+    launches_++;
+    if (reproject) {
+        Launch<R>::project_only(A_, stream_);
+        launches_++;
+    }
+    resort(false);
+    if (N > 0) one_step(true, nullptr, nullptr);
+    materialize();
+    HostViewOut32 o{dout, dout_i, dout_i + n, dout + 2 * n, dout + 5 * n, dout_i + 2 * n};
+    IoLaunch<R>::egest32(N, A_.cur, o, stream_);
+    launches_++;
+    // ---- outputs: chunk c of every array goes on the bus, an event marks it; the host widens chunk c while c+1 travels ----
+    DevCounters hc;
+    int nchunks = 0;
+    for (int c = 0; c < K; ++c) {
+        const size_t a = std::min(n, (size_t)c * cs), b = std::min(n, a + cs);
+        if (a == b) break;
+        for (int col = 0; col < 7; ++col)
+            CK(cudaMemcpyAsync(hout + col * n + a, dout + col * n + a, sizeof(float) * (b - a), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(heading + a, dout_i + a, sizeof(int) * (b - a), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(vid + a, dout_i + n + a, sizeof(int) * (b - a), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(color + a, dout_i + 2 * n + a, sizeof(int) * (b - a), cudaMemcpyDeviceToHost, stream_));
+        if (c == 0) CK(cudaMemcpyAsync(&hc, d_counters_.p, sizeof(hc), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaEventRecord(ev_chunk_[c], stream_));
+        nchunks++;
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t a = std::min(n, (size_t)c * cs), b = std::min(n, a + cs);
+        CK(cudaEventSynchronize(ev_chunk_[c]));
+        host_parallel(nt, [&](int t) {
+            const size_t len = b - a, ta = a + len * t / nt, tb = a + len * (t + 1) / nt;
+            for (int col = 0; col < 7; ++col) {
+                double* dst = col < 2 ? uv + col * n : (col < 5 ? r3d + (col - 2) * n : rdot + (col - 5) * n);
+                const float* src = hout + col * n;
+                size_t i = ta;
+#if defined(__SSE2__)
+                // streaming stores: the caller's arrays are written once and not read here — no write-allocate traffic
+                for (; i < tb && (((uintptr_t)(dst + i)) & 15); ++i) dst[i] = (double)src[i];
+                for (; i + 2 <= tb; i += 2) _mm_stream_pd(dst + i, _mm_set_pd((double)src[i + 1], (double)src[i]));
+#endif
+                for (; i < tb; ++i) dst[i] = (double)src[i];
+            }
+        });
+    }
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    int fault = N > 0 ? (int)hc.fault : 0;
+    if (fault) {
+        unsigned zero = 0;
+        CK(cudaMemcpyAsync(&d_counters_.p->fault, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream_));
+        CK(cudaStreamSynchronize(stream_));
+    }
     return fault;
 }
 

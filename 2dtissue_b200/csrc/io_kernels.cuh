@@ -125,6 +125,62 @@ __global__ void __launch_bounds__(256) k_egest(int resident, int N, const int* _
     if (out.new_heading) out.new_heading[o] = new_heading[s];
 }
 
+// fp32 staging for the host-buffer path of fp32 contexts (Engine::step_host32): the PCIe transfers carry floats, the widening
+// to the caller's doubles happens on host threads while the next chunk is in flight (float -> double is exact, so the caller
+// sees the same values as through k_egest)
+struct HostViewIn32 {
+    const float* uv;       // [2N]
+    const int* heading;    // [N]
+    const int* vid;        // [N] or null
+    const float* r3d;      // [3N] or null
+};
+struct HostViewOut32 {
+    float* uv;             // [2N]
+    int* heading;
+    int* vid;
+    float* r3d;            // [3N]
+    float* rdot;           // [2N]
+    int* color;
+};
+static __global__ void __launch_bounds__(256) k_ingest32(int N, HostViewIn32 in, ParticleArrays<float> p)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Real2<float> u = {in.uv[i], in.uv[N + i]};
+    p.uv[i] = u;
+    Pos3<float> X = {0.0f, 0.0f, 0.0f, (float)in.heading[i]};
+    if (in.r3d) {
+        X.x = in.r3d[i];
+        X.y = in.r3d[N + i];
+        X.z = in.r3d[2 * N + i];
+    }
+    p.pos[i] = X;
+    p.aux[i] = make_int4(in.vid ? in.vid[i] : 0, -1, i, i);
+    Real2<float> z = {0.0f, 0.0f};
+    p.rdot[i] = z;
+    p.color[i] = 0;
+}
+static __global__ void __launch_bounds__(256) k_egest32(int N, ParticleArrays<float> p, HostViewOut32 out)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const int4 ax = p.aux[s];
+    const int o = ax.w;
+    const Real2<float> u = p.uv[s];
+    out.uv[o] = u.x;
+    out.uv[N + o] = u.y;
+    out.vid[o] = ax.x;
+    const Pos3<float> X = p.pos[s];
+    out.heading[o] = (int)X.w;
+    out.r3d[o] = X.x;
+    out.r3d[N + o] = X.y;
+    out.r3d[2 * N + o] = X.z;
+    const Real2<float> r = p.rdot[s];
+    out.rdot[o] = r.x;
+    out.rdot[N + o] = r.y;
+    out.color[o] = p.color[s];
+}
+
 template <typename R> __global__ void __launch_bounds__(256) k_owned_flags(int n, ParticleArrays<R> p, int* flags)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,6 +216,8 @@ template <typename R> struct IoLaunch {
     static void seed(int N, uint64_t seed, int mode, uint32_t first_id, int F, const TriUV<R>* tri, const ParticleArrays<R>& p,
                      cudaStream_t s);
     static void owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s);
+    static void ingest32(int N, const HostViewIn32& in, const ParticleArrays<R>& p, cudaStream_t s);
+    static void egest32(int N, const ParticleArrays<R>& p, const HostViewOut32& out, cudaStream_t s);
     static void in2(int N, const double* src, Real2<R>* dst, cudaStream_t s);
     static void out2(int N, const Real2<R>* src, double* dst, cudaStream_t s);
     static void outN(int N, int cols, const R* src, double* dst, cudaStream_t s);
@@ -182,6 +240,18 @@ void IoLaunch<R>::seed(int N, uint64_t seed, int mode, uint32_t first_id, int F,
                        cudaStream_t s)
 {
     if (N > 0) k_seed<R><<<(N + 255) / 256, 256, 0, s>>>(N, seed, mode, first_id, F, tri, p);
+}
+template <typename R> void IoLaunch<R>::ingest32(int N, const HostViewIn32& in, const ParticleArrays<R>& p, cudaStream_t s)
+{
+    if constexpr (sizeof(R) == 4) {
+        if (N > 0) k_ingest32<<<(N + 255) / 256, 256, 0, s>>>(N, in, p);
+    }
+}
+template <typename R> void IoLaunch<R>::egest32(int N, const ParticleArrays<R>& p, const HostViewOut32& out, cudaStream_t s)
+{
+    if constexpr (sizeof(R) == 4) {
+        if (N > 0) k_egest32<<<(N + 255) / 256, 256, 0, s>>>(N, p, out);
+    }
 }
 template <typename R> void IoLaunch<R>::owned_flags(int n, const ParticleArrays<R>& p, int* flags, cudaStream_t s)
 {

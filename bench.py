@@ -390,8 +390,14 @@ def main_ours(args, rank, world, local_rank):
             ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col, reproject=True)
         barrier()
         e2e_s = time.perf_counter() - te
-        h2d = Nloc * (16 + 4)
-        d2h = Nloc * (16 + 4 + 4 + 24 + 16 + 4)
+        if spec["dtype"] == "f32":
+            # fp32 contexts: the caller's arrays are doubles in the reference's layouts, but the library narrows / widens them on
+            # host threads (Engine::step_host32) and the PCIe bus carries floats: uv + heading up, uv, r3d, rdot + 3 int arrays down
+            h2d = Nloc * (8 + 4)
+            d2h = Nloc * (8 + 12 + 8 + 4 + 4 + 4)
+        else:
+            h2d = Nloc * (16 + 4)
+            d2h = Nloc * (16 + 4 + 4 + 24 + 16 + 4)
     else:
         pinz = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()
         hb = dict(uv=pinz(2 * cap, torch.float64), n=pinz(cap, torch.int32), vid=pinz(cap, torch.int32),
