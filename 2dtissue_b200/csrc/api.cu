@@ -1176,6 +1176,7 @@ template <typename R> void Engine<R>::comm_phase1()
     for (int d = 0; d < 2; ++d) CK(cudaMemsetAsync(comm_send_[d].p, 0, 16, stream_));
     CK(cudaMemsetAsync(far_send_.p, 0, 16, stream_));
     prof_mark();
+    A_.lean = 0;   // slab mode: the step kernel keeps pos / uv / key (the classification and the messages are built from them)
     if (halo_valid_) {
         A_.step = (uint64_t)step_index;
         if (use_fast2_ && Launch<R>::step_fast2(A_, true, sm_count_, stream_))
@@ -1227,8 +1228,14 @@ template <typename R> void Engine<R>::comm_phase2()
     prof_mark();
     scan_buckets();
     prof_mark();
-    l2_window(A_.alt.pos);
-    Launch<R>::scatter(A_, stream_);
+    if (use_fast2_ && lean_ok_) {   // lean sort: record + aux + source index; materialize() rebuilds the rest on demand
+        Launch<R>::scatter_lean(A_, stream_);
+        lean_ = true;
+    } else {
+        l2_window(A_.alt.pos);
+        Launch<R>::scatter(A_, stream_);
+        lean_ = false;
+    }
     std::swap(A_.cur, A_.alt);
     launches_ += 2;
     prof_mark();

@@ -324,12 +324,32 @@ static __global__ void __launch_bounds__(256) k_scatter_lean(StepArgs<float> a)
     a.alt.aux[s] = a.cur.aux[i];
     a.src[s] = i;
 }
+// The same in slab mode: the step kernel and the unpack kernels leave pos / uv / key in the pre-sort arrays (the slab
+// classification needs them), halo copies of the previous step and leavers carry KEY_DROP, and the resident count lives on
+// the device.  Still only record + aux + source index are written in bucket order.
+static __global__ void __launch_bounds__(256) k_scatter_lean_comm(StepArgs<float> a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.comm.state->n_res;
+    if (i == 0) a.comm.state->n = a.start[a.M];   // residents after this sort (nobody reads n in this kernel)
+    if (i >= n) return;
+    const uint32_t key = a.key[i];
+    if (key == KEY_DROP) return;
+    const int s = a.start[key] + (int)a.rank[i];
+    const Pos3<float> P = a.cur.pos[i];
+    const Real2<float> U = a.cur.uv[i];
+    const int h = (int)P.w;
+    a.alt.rec[2 * (size_t)s] = make_float4(P.x, P.y, P.z, __int_as_float((unsigned)h <= 360u ? h : 362));
+    a.alt.rec[2 * (size_t)s + 1] = make_float4(U.x, U.y, __int_as_float((int)key), __int_as_float(h));
+    a.alt.aux[s] = a.cur.aux[i];
+    a.src[s] = i;
+}
 // the full sorted state from the lean one: pos / uv from the record, r_dot / colour through the source index
 // (a.alt = the pre-sort side that the last step kernel wrote)
 static __global__ void __launch_bounds__(256) k_expand(StepArgs<float> a)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.N) return;
+    if (s >= (a.comm.on ? a.comm.state->n : a.N)) return;
     const float4 r0 = a.cur.rec[2 * (size_t)s], r1 = a.cur.rec[2 * (size_t)s + 1];
     const Pos3<float> P = {r0.x, r0.y, r0.z, (float)__float_as_int(r1.w)};
     const Real2<float> U = {r1.x, r1.y};
@@ -1657,13 +1677,19 @@ template <typename R> void Launch<R>::scatter(const StepArgs<R>& a, cudaStream_t
 template <typename R> void Launch<R>::scatter_lean(const StepArgs<R>& a, cudaStream_t s)
 {
     if constexpr (sizeof(R) == 4) {
-        if (a.N > 0) k_scatter_lean<<<div_up(a.N, 256), 256, 0, s>>>(a);
+        const int n = launch_extent<R>(a);
+        if (n <= 0) return;
+        if (a.comm.on)
+            k_scatter_lean_comm<<<div_up(n, 256), 256, 0, s>>>(a);
+        else
+            k_scatter_lean<<<div_up(n, 256), 256, 0, s>>>(a);
     }
 }
 template <typename R> void Launch<R>::expand(const StepArgs<R>& a, cudaStream_t s)
 {
     if constexpr (sizeof(R) == 4) {
-        if (a.N > 0) k_expand<<<div_up(a.N, 256), 256, 0, s>>>(a);
+        const int n = launch_extent<R>(a);
+        if (n > 0) k_expand<<<div_up(n, 256), 256, 0, s>>>(a);
     }
 }
 template <typename R> void Launch<R>::step_euclid(const StepArgs<R>& a, bool moving, cudaStream_t s)

@@ -251,6 +251,50 @@ def main_reference(args, rank, world):
     emit(json.dumps(line))
 
 
+def transport_parity_check(t2d, dist, rank, world, local_rank):
+    """Slab runs only, before the timed workload: a small fp64 problem is stepped (a) by `world` ranks over
+    the NCCL transport and (b), on rank 0, by one single context; the merged NCCL result must equal (b) BIT FOR BIT (global ids
+    travel with the particles, the exact path sums in ascending id).  So every scaling line this bench prints also proves that
+    the transport it timed moves the right particles.  Returns a small dict for the JSON line."""
+    chart = load_chart(t2d, 0)
+    N, steps = 40000, 5
+    uv, n = t2d.seed_particles(N, seed=41)
+    sigma = sigma_for(N)
+    kw = dict(v0=0.1, k=1.0, sigma=sigma, step_size=0.001, eta=0.03, seed=5, neigh_mode=t2d.NEIGH_EUCLID,
+              precision=t2d.PRECISION_FP64, device=local_rank)
+    c0 = t2d.Context(chart, capacity=N, **kw)
+    c0.set_particles(uv, n)
+    s0 = c0.download(("uv", "n", "vid", "r3d"))
+    ref = None
+    if rank == 0:
+        c0.step(steps)
+        ref = c0.download()
+    c0.close()
+    cuts = t2d.slab_cuts(s0["r3d"][:N], world)
+    uid = [t2d.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = t2d.Context(chart, capacity=N, **kw)
+    ctx.comm_init(rank, world, uid[0], cuts)
+    p = t2d.partition_by_slab(s0, cuts, rank)
+    ctx.set_state(p["uv"], p["n"], p["vid"], p["r3d"], ids=p["ids"])
+    fault = ctx.step(steps)
+    part = ctx.download()
+    part["ids"] = ctx.download_ids()
+    ctx.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, part)
+    res = None
+    if rank == 0:
+        out = t2d.merge_by_id(parts, N)
+        bad = {k: int(np.sum(out[k] != ref[k])) for k in ("n", "vid", "face", "color", "uv", "rdot", "r3d")}
+        res = {"ok": fault == 0 and sum(q["ids"].size for q in parts) == N and not any(bad.values()),
+               "what": "fp64, %d particles, %d steps, %d NCCL slabs vs one context: bit-identical" % (N, steps, world),
+               "owned": [int(q["ids"].size) for q in parts], "mismatches": bad}
+        if not res["ok"]:
+            sys.stderr.write("transport parity check FAILED: %s\n" % json.dumps(res))
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
@@ -275,6 +319,7 @@ def main_ours(args, rank, world, local_rank):
     slabs = world > 1 and not replicas
     if slabs and mode != t2d.NEIGH_EUCLID:
         raise SystemExit("multi-GPU slabs support the Euclidean criterion (workloads c4shard / c2)")
+    parity = transport_parity_check(t2d, dist, rank, world, local_rank) if slabs else None
     cap = int(Nloc * 1.25) + 65536 if slabs else Nloc      # room for halo copies and migration imbalance
     kw = dict(v0=0.1, k=spec.get("k", 1.0), sigma=sigma, step_size=0.001, neigh_mode=mode, precision=prec, capacity=cap, device=local_rank,
               lift_mode=t2d.LIFT_BARYCENTRIC if args.lift == "barycentric" else t2d.LIFT_REFERENCE)
@@ -454,6 +499,7 @@ def main_ours(args, rank, world, local_rank):
                                "(2/3/3/4 levels at 1/2/4/8 GPUs) and sigma follows the total particle count, so the per-GPU work "
                                "is similar, not identical, along the curve"} if args.workload == "c4shard" else {})},
                 "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
+                **({"transport_parity": parity} if parity is not None else {}),
                 "kernel_ms": prof, "roofline": roof,
                 "cpu_baseline": cb,
                 "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d * world),
