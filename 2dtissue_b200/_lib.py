@@ -42,7 +42,7 @@ class Counters(C.Structure):
 # every symbol include/t2d.h declares (tests/test_abi.py checks the built library exports all of them)
 SYMBOLS = [
     "t2d_create", "t2d_destroy", "t2d_last_error", "t2d_version", "t2d_set_particles", "t2d_set_state", "t2d_download",
-    "t2d_seed_particles", "t2d_particle_count", "t2d_step", "t2d_step_host", "t2d_step_host_uv", "t2d_observables", "t2d_get_counters", "t2d_reset_counters", "t2d_set_tie_log",
+    "t2d_seed_particles", "t2d_export_begin", "t2d_export_wait", "t2d_particle_count", "t2d_step", "t2d_step_host", "t2d_step_host_uv", "t2d_observables", "t2d_get_counters", "t2d_reset_counters", "t2d_set_tie_log",
     "t2d_get_step", "t2d_set_step", "t2d_set_params", "t2d_get_r3d", "t2d_tiling", "t2d_angles_to_unit_vectors",
     "t2d_forces", "t2d_build_hop_table", "t2d_last_step_ms", "t2d_profile_step", "t2d_pinned_alloc", "t2d_pinned_free",
     "t2d_comm_unique_id", "t2d_comm_init", "t2d_comm_init_local", "t2d_step_local", "t2d_comm_destroy", "t2d_owned_count",
@@ -78,6 +78,9 @@ def load():
     L.t2d_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.t2d_reset_counters.argtypes = [vp]
     L.t2d_set_tie_log.argtypes = [vp, C.c_int]
+    L.t2d_export_begin.argtypes = [vp, C.POINTER(C.c_int32)]
+    pdp, pip = C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_int32))
+    L.t2d_export_wait.argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64), pdp, pip, pip, pdp, pdp, pip]
     L.t2d_seed_particles.argtypes = [vp, C.c_int32, C.c_uint64, C.c_int32, C.c_uint32]
     L.t2d_get_step.argtypes = [vp]
     L.t2d_get_step.restype = C.c_int64

@@ -91,6 +91,9 @@ struct EngineBase {
     virtual int reset_counters() = 0;
     virtual int set_tie_log(int on) = 0;
     virtual int seed_particles(int N, uint64_t seed, int mode, uint32_t first_id) = 0;
+    virtual int export_begin(int* slot) = 0;
+    virtual int export_wait(int slot, int* N, long long* step, const double** uv, const int** heading, const int** vid,
+                            const double** r3d, const double** rdot, const int** color) = 0;
     virtual int set_params(const t2d_params* p) = 0;
     virtual int get_r3d(int N, const double* uv, double* r3d, int* vid, int* face) = 0;
     virtual int tiling(int N, double* uv_old, double* uv, int* heading) = 0;
@@ -158,6 +161,9 @@ template <typename R> class Engine : public EngineBase {
     int get_counters(t2d_counters* out) override;
     int reset_counters() override;
     int seed_particles(int N, uint64_t seed, int mode, uint32_t first_id) override;
+    int export_begin(int* slot) override;
+    int export_wait(int slot, int* N, long long* step, const double** uv, const int** heading, const int** vid, const double** r3d,
+                    const double** rdot, const int** color) override;
     int set_tie_log(int on) override
     {
         A_.count_ties = on ? 1 : 0;
@@ -246,6 +252,14 @@ template <typename R> class Engine : public EngineBase {
     bool lean_ok_ = false;                       // the lean pipeline may be used (fp32 Euclid fast path; T2D_LEAN=0 switches it off)
     void scan_buckets();
     void materialize();
+    // asynchronous export: two slots of {device staging, pinned host buffer, "copied" event} and a side stream
+    cudaStream_t export_stream_ = nullptr;
+    unsigned char* h_export_[2] = {nullptr, nullptr};
+    DevBuf<unsigned char> d_export_[2];
+    cudaEvent_t ev_export_snap_[2] = {}, ev_export_done_[2] = {};
+    int export_n_[2] = {0, 0};
+    long long export_step_[2] = {0, 0};
+    unsigned export_seq_ = 0;
     // host-buffer path of fp32 contexts: float staging + widening on host threads, chunked so that it overlaps the transfers
     float* h32_ = nullptr;          // pinned: [5N] in (uv, r3d) followed by [7N] out (uv, r3d, rdot)
     size_t h32_cap_ = 0;            // particles the pinned staging holds
@@ -444,6 +458,12 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
 template <typename R> Engine<R>::~Engine()
 {
     if (h32_) cudaFreeHost(h32_);
+    for (int k = 0; k < 2; ++k) {
+        if (h_export_[k]) cudaFreeHost(h_export_[k]);
+        if (ev_export_snap_[k]) cudaEventDestroy(ev_export_snap_[k]);
+        if (ev_export_done_[k]) cudaEventDestroy(ev_export_done_[k]);
+    }
+    if (export_stream_) cudaStreamDestroy(export_stream_);
     for (auto& e : ev_chunk_)
         if (e) cudaEventDestroy(e);
     closing_ = true;
@@ -1390,6 +1410,69 @@ int Engine<R>::step_host(int N, double* uv, int* heading, int* vid, double* r3d,
     return fault;
 }
 
+// ---- asynchronous export (include/t2d.h t2d_export_begin / t2d_export_wait) ------------------------------------------
+// layout of one slot (device staging and pinned host buffer alike): uv [2N] double, r3d [3N], rdot [2N], then heading, vid,
+// colour [N] int each
+template <typename R> int Engine<R>::export_begin(int* slot)
+{
+    if (comm_on_) throw CudaError{"t2d_export_begin is not available in slab mode"};
+    CK(cudaSetDevice(device_));
+    const size_t C = (size_t)capacity_, bytes = C * (7 * sizeof(double) + 3 * sizeof(int)) + 64;
+    if (!export_stream_) {
+        CK(cudaStreamCreateWithFlags(&export_stream_, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaHostAlloc((void**)&h_export_[k], bytes, cudaHostAllocDefault));
+            d_export_[k].alloc(bytes);
+            CK(cudaEventCreateWithFlags(&ev_export_snap_[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_export_done_[k], cudaEventDisableTiming));
+            CK(cudaEventRecord(ev_export_done_[k], export_stream_));
+        }
+    }
+    const int k = (int)(export_seq_++ & 1u);
+    const size_t N = (size_t)this->N;
+    materialize();
+    CK(cudaStreamWaitEvent(stream_, ev_export_done_[k], 0));   // the slot's previous copy has left the staging buffer
+    unsigned char* base = d_export_[k].p;
+    HostViewOut o{};
+    o.uv = (double*)base;
+    o.r3d = o.uv + 2 * N;
+    o.rdot = o.r3d + 3 * N;
+    o.heading = (int*)(o.rdot + 2 * N);
+    o.vid = o.heading + N;
+    o.color = o.vid + N;
+    IoLaunch<R>::egest((int)N, (int)N, nullptr, A_.cur, A_.F, A_.new_heading, o, stream_);
+    launches_++;
+    CK(cudaEventRecord(ev_export_snap_[k], stream_));
+    CK(cudaStreamWaitEvent(export_stream_, ev_export_snap_[k], 0));
+    CK(cudaMemcpyAsync(h_export_[k], base, N * (7 * sizeof(double) + 3 * sizeof(int)), cudaMemcpyDeviceToHost, export_stream_));
+    CK(cudaEventRecord(ev_export_done_[k], export_stream_));
+    export_n_[k] = (int)N;
+    export_step_[k] = step_index;
+    if (slot) *slot = k;
+    return 0;
+}
+
+template <typename R>
+int Engine<R>::export_wait(int slot, int* N, long long* step, const double** uv, const int** heading, const int** vid,
+                           const double** r3d, const double** rdot, const int** color)
+{
+    if (slot < 0 || slot > 1 || !export_stream_) throw CudaError{"t2d_export_wait: no such export in flight"};
+    CK(cudaSetDevice(device_));
+    CK(cudaEventSynchronize(ev_export_done_[slot]));
+    const size_t n = (size_t)export_n_[slot];
+    const double* base = (const double*)h_export_[slot];
+    if (N) *N = (int)n;
+    if (step) *step = export_step_[slot];
+    if (uv) *uv = base;
+    if (r3d) *r3d = base + 2 * n;
+    if (rdot) *rdot = base + 5 * n;
+    const int* ib = (const int*)(base + 7 * n);
+    if (heading) *heading = ib;
+    if (vid) *vid = ib + n;
+    if (color) *color = ib + 2 * n;
+    return 0;
+}
+
 // run fn(t) for t = 0 .. nt-1 on host threads (OpenMP keeps its pool alive between calls; num_threads overrides the
 // OMP_NUM_THREADS=1 that torchrun exports)
 static void host_parallel(int nt, const std::function<void(int)>& fn)
@@ -1414,6 +1497,12 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
     const size_t n = (size_t)N;
     if (h32_cap_ < n) {
         if (h32_) cudaFreeHost(h32_);
+    for (int k = 0; k < 2; ++k) {
+        if (h_export_[k]) cudaFreeHost(h_export_[k]);
+        if (ev_export_snap_[k]) cudaEventDestroy(ev_export_snap_[k]);
+        if (ev_export_done_[k]) cudaEventDestroy(ev_export_done_[k]);
+    }
+    if (export_stream_) cudaStreamDestroy(export_stream_);
         h32_ = nullptr;
         CK(cudaHostAlloc((void**)&h32_, sizeof(float) * 12 * (size_t)capacity_, cudaHostAllocDefault));
         h32_cap_ = (size_t)capacity_;
@@ -1814,6 +1903,23 @@ int t2d_observables(t2d_ctx* ctx, double out[T2D_OBS_LEN]) { T2D_TRY(ctx, return
 int t2d_get_counters(t2d_ctx* ctx, t2d_counters* out) { T2D_TRY(ctx, return ctx->eng->get_counters(out);) }
 int t2d_reset_counters(t2d_ctx* ctx) { T2D_TRY(ctx, return ctx->eng->reset_counters();) }
 int t2d_set_tie_log(t2d_ctx* ctx, int on) { T2D_TRY(ctx, return ctx->eng->set_tie_log(on);) }
+int t2d_export_begin(t2d_ctx* ctx, int32_t* slot)
+{
+    int k = 0;
+    T2D_TRY(ctx, { int rc = ctx->eng->export_begin(&k); if (slot) *slot = k; return rc; })
+}
+int t2d_export_wait(t2d_ctx* ctx, int32_t slot, int32_t* N, int64_t* step, const double** uv, const int32_t** heading,
+                    const int32_t** vid, const double** r3d, const double** rdot, const int32_t** color)
+{
+    long long st = 0;
+    int n = 0;
+    T2D_TRY(ctx, {
+        int rc = ctx->eng->export_wait(slot, &n, &st, uv, heading, vid, r3d, rdot, color);
+        if (N) *N = n;
+        if (step) *step = st;
+        return rc;
+    })
+}
 int t2d_seed_particles(t2d_ctx* ctx, int32_t N, uint64_t seed, int32_t mode, uint32_t first_id)
 {
     T2D_TRY(ctx, return ctx->eng->seed_particles(N, seed, mode, first_id);)

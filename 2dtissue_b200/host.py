@@ -176,6 +176,23 @@ class Context:
     def step(self, nsteps=1):
         return self._chk(self.L.t2d_step(self.h, nsteps), "t2d_step")
 
+    def export_begin(self):
+        """Start an asynchronous snapshot + device->pinned-host copy of the resident state on a side stream; returns a slot."""
+        slot = C.c_int32(0)
+        self._chk(self.L.t2d_export_begin(self.h, C.byref(slot)), "t2d_export_begin")
+        return slot.value
+
+    def export_wait(self, slot):
+        """Block until the slot's copy has landed; numpy views into the pinned ring (valid until the slot is reused)."""
+        N, step = C.c_int32(0), C.c_int64(0)
+        uv, r3d, rdot = C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+        n, vid, col = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        self._chk(self.L.t2d_export_wait(self.h, slot, C.byref(N), C.byref(step), C.byref(uv), C.byref(n), C.byref(vid), C.byref(r3d),
+                                         C.byref(rdot), C.byref(col)), "t2d_export_wait")
+        m = N.value
+        view = lambda p, k: np.ctypeslib.as_array(p, shape=(k * m,)) if m else np.zeros(0)
+        return dict(step=step.value, uv=view(uv, 2), n=view(n, 1), vid=view(vid, 1), r3d=view(r3d, 3), rdot=view(rdot, 2), color=view(col, 1))
+
     def step_host(self, uv, heading, vid, r3d, rdot, color, reproject=False):
         """In/out numpy arrays in the reference's layouts (the literal perform_particle_simulation drop-in).
         reproject=True: only uv and heading are uploaded, the device re-projects uv (vid, r3d are outputs only)."""

@@ -26,7 +26,9 @@ static void usage(const char* argv0)
               << "  --kafka                        not available in this build\n"
               << " extensions:\n"
               << "  --neigh {table,euclid}  --precision {fp64,fp32}  --lift {reference,barycentric}  --sigma X  --noise-eta X  --seed N  --device N\n"
-              << "  --data-dir DIR  --load-state FILE  --save-state FILE  --dump-chart FILE  --no-particles  --quiet\n";
+              << "  --data-dir DIR  --load-state FILE  --save-state FILE  --dump-chart FILE  --no-particles  --quiet\n"
+              << "  --export-every K               export / CSV of every K-th step only, copied asynchronously beside the steps\n"
+              << "  --device-seed                  seed the particles on the GPU (Philox) instead of mt19937 on the host\n";
 }
 
 int main(int argc, char* argv[])
@@ -64,6 +66,8 @@ int main(int argc, char* argv[])
             else if (a == "--dump-chart") dump_chart = val();
             else if (a == "--no-particles") ext.export_particles = false;
             else if (a == "--quiet") ext.quiet = true;
+            else if (a == "--export-every") ext.export_every = std::max(1, std::stoi(val()));
+            else if (a == "--device-seed") ext.device_seed = true;
             else if (a == "-h" || a == "--help") { usage(argv[0]); return 0; }
             else throw std::runtime_error("Unknown argument: " + a);
         }
@@ -83,9 +87,18 @@ int main(int argc, char* argv[])
                      1, 1, 0.75, 0.001, 30, ext);
         sim.start();
         const auto t0 = std::chrono::steady_clock::now();
-        while (!sim.is_finished()) {
-            System data = sim.update();
-            (void)data;
+        if (ext.export_every > 1) {   // every-k cadence: asynchronous export, the copy of block b overlaps the steps of block b + 1
+            while (!sim.is_finished()) {
+                System data = sim.update_block(ext.export_every);
+                (void)data;
+            }
+            System last = sim.flush_export();
+            (void)last;
+        } else {
+            while (!sim.is_finished()) {
+                System data = sim.update();
+                (void)data;
+            }
         }
         for (double v : sim.get_order_parameter()) std::cout << v << '\n';
         const double duration = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -94,6 +94,10 @@ void Tissue2D::start()
         if (!in) throw std::runtime_error("truncated state file " + ext_.load_state);
         current_step = (int)hdr[1];
         t2d_set_step(gpu, hdr[1]);
+    } else if (ext_.device_seed) {   // seeding + initial projection on the GPU: face centres like CellHelper::init_particle_position
+        check(t2d_seed_particles(gpu, particle_count, ext_.seed ? ext_.seed : 1234, /*mode*/ 1, 0), "t2d_seed_particles");
+        check(t2d_download(gpu, r_UV.data(), n.data(), vertices_3D_active.data(), r_3D.data(), nullptr, nullptr, nullptr), "t2d_download");
+        return;
     } else {
         init_particle_position();
     }
@@ -148,6 +152,85 @@ System Tissue2D::update()
     if (current_step >= step_count) finished = true;
     if (save_data) save_our_data();
     return system;
+}
+
+// ---- every-k cadence with the asynchronous export (include/t2d.h t2d_export_begin / t2d_export_wait) ----
+System Tissue2D::collect_export(int slot)
+{
+    System system{};
+    int32_t N = 0;
+    int64_t step = 0;
+    const double *uv = nullptr, *r3d = nullptr, *rdot = nullptr;
+    const int32_t *h = nullptr, *vid = nullptr, *col = nullptr;
+    check(t2d_export_wait(gpu, slot, &N, &step, &uv, &h, &vid, &r3d, &rdot, &col), "t2d_export_wait");
+    const size_t n = (size_t)N;
+    std::copy(uv, uv + 2 * n, r_UV.begin());
+    std::copy(r3d, r3d + 3 * n, r_3D.begin());
+    std::copy(rdot, rdot + 2 * n, r_dot.begin());
+    std::copy(h, h + n, this->n.begin());
+    std::copy(vid, vid + n, vertices_3D_active.begin());
+    std::copy(col, col + n, particles_color.begin());
+    const int idx = (int)step - 1;
+    system.order_parameter = (idx >= 0 && idx < (int)v_order.size()) ? v_order[(size_t)idx] : 0.0;
+    if (ext_.export_particles) {
+        system.particles.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            Particle p{};
+            p.x_UV = r_UV[i];
+            p.y_UV = r_UV[n + i];
+            p.x_velocity_UV = r_dot[i];
+            p.y_velocity_UV = r_dot[n + i];
+            p.alignment_UV = this->n[i];
+            p.x_3D = r_3D[i];
+            p.y_3D = r_3D[n + i];
+            p.z_3D = r_3D[2 * n + i];
+            p.neighbor_count = particles_color[i];
+            system.particles[i] = p;
+        }
+    }
+    if (save_data) {
+        const int keep = current_step;
+        current_step = (int)step;     // file names carry the step the snapshot belongs to
+        save_our_data();
+        current_step = keep;
+    }
+    return system;
+}
+
+System Tissue2D::update_block(int k)
+{
+    k = std::max(1, std::min(k, step_count - current_step));
+    if (!ext_.quiet) std::cout << "Steps: " << current_step << " .. " << current_step + k - 1 << "\n";
+    // the order parameter is a by-product of every step (cheap: one reduction); the state export is not
+    for (int s = 0; s < k; ++s) {
+        const int fault = t2d_step(gpu, 1);
+        check(fault, "t2d_step");
+        if (fault & T2D_FAULT_LOST) throw std::runtime_error("We lost particles after getting the original UV mesh coord");
+        if (fault & T2D_FAULT_NONFINITE) {
+            std::cerr << "Invalid values (NaN or Inf) in the particle positions\n";
+            std::exit(1);
+        }
+        if (fault & T2D_FAULT_WRAP_CAP) throw std::runtime_error("seam re-entry did not terminate (EuclideanTiling)");
+        double obs[T2D_OBS_LEN];
+        check(t2d_observables(gpu, obs), "t2d_observables");
+        if (current_step < (int)v_order.size()) v_order[(size_t)current_step] = obs[T2D_OBS_PHI];
+        current_step++;
+    }
+    int32_t slot = -1;
+    check(t2d_export_begin(gpu, &slot), "t2d_export_begin");   // returns at once: the copy runs beside the next block
+    System landed{};
+    if (pending_slot_ >= 0) landed = collect_export(pending_slot_);   // the block before this one, while this one's copy travels
+    pending_slot_ = slot;
+    if (current_step >= step_count) finished = true;
+    return landed;
+}
+
+System Tissue2D::flush_export()
+{
+    System s{};
+    if (pending_slot_ >= 0) s = collect_export(pending_slot_);
+    pending_slot_ = -1;
+    return s;
 }
 
 bool Tissue2D::is_finished() { return finished; }

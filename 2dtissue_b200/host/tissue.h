@@ -44,6 +44,9 @@ struct Extensions {
     std::string load_state;                // binary state to start from instead of init_particle_position
     bool export_particles = true;          // build the Particle vector every step like update() does
     bool quiet = false;                    // suppress the reference's per-step "Step: i" print
+    int export_every = 1;                  // --export-every k: the Particle export / CSV of every k-th step only, fetched by
+                                           // the asynchronous export (side stream + pinned ring) while the next k steps run
+    bool device_seed = false;              // --device-seed: t2d_seed_particles (Philox on the GPU) instead of mt19937 on the host
 };
 
 class Tissue2D {
@@ -58,6 +61,10 @@ class Tissue2D {
 
     void start();
     System update();
+    // k steps on the device with the previous export's copy still in flight, then the snapshot of this block is started;
+    // returns the export that has just landed (the block before), empty for the first block.  run() uses it when export_every > 1
+    System update_block(int k);
+    System flush_export();   // the last block's export
     bool is_finished();
     std::vector<double> get_order_parameter();
 
@@ -69,6 +76,8 @@ class Tissue2D {
   private:
     void init_particle_position();   // CellHelper::init_particle_position, CellHelper.cpp:43-67
     void save_our_data();            // _2DTissue::save_our_data, 2DTissue.cpp:270-280
+    System collect_export(int slot);
+    int pending_slot_ = -1;
     void check(int rc, const char* what);
 
     bool save_data;

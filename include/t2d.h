@@ -151,6 +151,15 @@ int t2d_seed_particles(t2d_ctx* ctx, int32_t N, uint64_t seed, int32_t mode, uin
 /* full state injection (uv, heading, vid, r3d as a previous step left them); used by t2d_step_host */
 int t2d_set_state(t2d_ctx* ctx, int32_t N, const double* uv, const int32_t* heading, const int32_t* vid,
                   const double* r3d, const uint32_t* ids);
+/* Asynchronous export (the output path of _2DTissue::update, 2DTissue.cpp:148-162, 270-280, without stalling the step):
+ * t2d_export_begin snapshots the resident state into a device staging buffer on the step stream and starts its copy into
+ * a pinned host ring on a SIDE stream; it returns at once with a slot number (two slots), and the caller keeps stepping.
+ * t2d_export_wait blocks until that slot's copy has landed and hands out pointers into the pinned ring, in the reference's
+ * layouts (r_UV and r_dot N x 2 column-major, r_3D N x 3, n, vertices_3D_active, particles_color); they stay valid until the
+ * slot is reused by the second t2d_export_begin after this one.  Single-context mode only. */
+int t2d_export_begin(t2d_ctx* ctx, int32_t* slot);
+int t2d_export_wait(t2d_ctx* ctx, int32_t slot, int32_t* N, int64_t* step, const double** uv, const int32_t** heading,
+                    const int32_t** vid, const double** r3d, const double** rdot, const int32_t** color);
 /* any output pointer may be NULL.  Order = the order of the last upload (ascending position in ids). */
 int t2d_download(t2d_ctx* ctx, double* uv, int32_t* heading, int32_t* vid, double* r3d, double* rdot, int32_t* color,
                  int32_t* face);

@@ -543,3 +543,30 @@ def test_device_side_seeding(t2d, chart):
     assert np.allclose(np.stack([s["uv"][:5000], s["uv"][5000:]], axis=1), uvc[f], atol=1e-12)
     assert len(np.unique(f)) > 0.3 * min(5000, len(uvc))
     ctx.close()
+
+
+def test_async_export_matches_download(t2d, chart):
+    """Row f2: t2d_export_begin / t2d_export_wait — the snapshot travels on a side stream into a pinned ring while the context
+    keeps stepping; what arrives is exactly what a blocking t2d_download at the same step returns."""
+    N = 50_000
+    sigma = float(np.sqrt(0.5 * 451.3 / (np.pi * N)))
+    uv, n = t2d.seed_particles(N, seed=3)
+    for prec in (t2d.PRECISION_FP32, t2d.PRECISION_FP64):
+        ctx = t2d.Context(chart, sigma=sigma, neigh_mode=t2d.NEIGH_EUCLID, precision=prec, capacity=N)
+        ctx.set_particles(uv, n)
+        snaps = []
+        for k in range(3):                       # export every 4 steps, keep stepping while the copy is in flight
+            assert ctx.step(4) == 0
+            ref = ctx.download()
+            slot = ctx.export_begin()
+            snaps.append((slot, ref, ctx.step_index))
+            if k > 0:                            # the previous export is consumed one cadence later, like a writer thread would
+                pslot, pref, pstep = snaps[k - 1]
+                got = ctx.export_wait(pslot)
+                assert got["step"] == pstep
+                for key in ("uv", "n", "vid", "r3d", "rdot", "color"):
+                    assert np.array_equal(got[key], pref[key]), key
+        got = ctx.export_wait(snaps[-1][0])
+        for key in ("uv", "n", "vid", "r3d", "rdot", "color"):
+            assert np.array_equal(got[key], snaps[-1][1][key]), key
+        ctx.close()

@@ -112,3 +112,37 @@ def test_driver_equals_python_host(sim, t2d, chart, hop_table, tmp_path, neigh):
     ref2 = ctx.download()
     uv3, n3, step3 = read_state(s_out2)
     assert step3 == steps + 3 and np.array_equal(uv3, ref2["uv"]) and np.array_equal(n3, ref2["n"])
+
+
+@pytest.mark.gpu
+def test_driver_export_every_k_async(sim, t2d, chart, tmp_path):
+    """Row f2: --export-every k — the CSV export of every k-th step only, fetched by the asynchronous export (side stream +
+    pinned ring) while the next block runs; the files equal what the Python host downloads at those steps, and the final
+    state equals a straight run.  --device-seed starts from t2d_seed_particles."""
+    N, steps, k = 800, 12, 4
+    uv, n = t2d.seed_particles(N, seed=12)
+    s_in, s_out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    write_state(s_in, uv, n)
+    data_dir = tmp_path / "data"
+    data_dir.mkdir()
+    r = subprocess.run([sim, "--mesh-path", CHART, "--particle-count", str(N), "--step-count", str(steps), "--step-time", "0.02",
+                        "--neigh", "euclid", "--sigma", "0.3", "--load-state", s_in, "--save-state", s_out, "--save-data",
+                        "--data-dir", str(data_dir), "--export-every", str(k), "--no-particles"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Steps: 0 .. 3" in r.stdout and "Steps: 8 .. 11" in r.stdout
+    ctx = t2d.Context(chart, v0=0.02, sigma=0.3, neigh_mode=t2d.NEIGH_EUCLID, capacity=N)
+    ctx.set_particles(uv, n)
+    for b in range(steps // k):
+        assert ctx.step(k) == 0
+        ref = ctx.download()
+        step = (b + 1) * k
+        got = np.loadtxt(data_dir / ("r_data_%d.csv" % step), delimiter=",")
+        assert got.shape == (N, 2) and np.allclose(got[:, 0], ref["uv"][:N], rtol=1e-14, atol=1e-15)
+        col = np.loadtxt(data_dir / ("particles_color_%d.csv" % step), delimiter=",")
+        assert np.array_equal(col.astype(np.int32), ref["color"])
+    assert not (data_dir / "r_data_5.csv").exists()
+    uv2, n2, step = read_state(s_out)
+    assert step == steps and np.array_equal(uv2, ref["uv"]) and np.array_equal(n2, ref["n"])
+    r = subprocess.run([sim, "--mesh-path", CHART, "--particle-count", "300", "--step-count", "3", "--neigh", "euclid", "--sigma", "0.3",
+                        "--device-seed", "--seed", "7", "--quiet", "--no-particles"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
