@@ -28,6 +28,7 @@ static void usage(const char* argv0)
               << "  --neigh {table,euclid}  --precision {fp64,fp32}  --lift {reference,barycentric}  --sigma X  --noise-eta X  --seed N  --device N\n"
               << "  --data-dir DIR  --load-state FILE  --save-state FILE  --dump-chart FILE  --no-particles  --quiet\n"
               << "  --export-every K               export / CSV of every K-th step only, copied asynchronously beside the steps\n"
+              << "  --table FILE                   table criterion from a T2DCSR1 cache (hop counts or metric geodesic rows, 2dtissue_b200/table.py)\n"
               << "  --device-seed                  seed the particles on the GPU (Philox) instead of mt19937 on the host\n";
 }
 
@@ -68,6 +69,7 @@ int main(int argc, char* argv[])
             else if (a == "--quiet") ext.quiet = true;
             else if (a == "--export-every") ext.export_every = std::max(1, std::stoi(val()));
             else if (a == "--device-seed") ext.device_seed = true;
+            else if (a == "--table") ext.table_cache = val();
             else if (a == "-h" || a == "--help") { usage(argv[0]); return 0; }
             else throw std::runtime_error("Unknown argument: " + a);
         }

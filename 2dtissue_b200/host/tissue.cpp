@@ -27,6 +27,32 @@ Tissue2D::Tissue2D(bool save_data_, bool particle_innenleben, bool free_boundary
     // table criterion: the reference's hop-count table (CachedGeodesicDistanceHelper, 2DTissue.cpp:102-105) is built on
     // the GPU from the chart's edge graph instead of being parsed from a 44 MB CSV
     t2d_table table{chart_.V, ext_.neigh_mode == T2D_NEIGH_TABLE ? T2D_TABLE_HOPS_FROM_MESH : T2D_TABLE_NONE, nullptr};
+    // --table FILE: thresholded rows from the binary cache (replaces the reference's CSV cache, CachedGeodesicDistanceHelper.h:22-72)
+    std::vector<int32_t> c_start, c_col;
+    std::vector<unsigned char> c_val;
+    t2d_table_csr csr{};
+    if (ext_.neigh_mode == T2D_NEIGH_TABLE && !ext_.table_cache.empty()) {
+        std::ifstream in(ext_.table_cache, std::ios::binary);
+        char magic[8];
+        int64_t hdr[2], item = 0;
+        double radius = 0;
+        in.read(magic, 8);
+        in.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
+        in.read(reinterpret_cast<char*>(&radius), sizeof(radius));
+        in.read(reinterpret_cast<char*>(&item), sizeof(item));
+        if (!in || std::string(magic, 8) != std::string("T2DCSR1\0", 8) || hdr[0] != chart_.V || (item != 8 && item != 4 && item != 1))
+            throw std::runtime_error("cannot read the table cache " + ext_.table_cache + " (missing, not T2DCSR1, or for another mesh)");
+        c_start.resize((size_t)hdr[0] + 1);
+        c_col.resize((size_t)hdr[1]);
+        c_val.resize((size_t)hdr[1] * (size_t)item);
+        in.read(reinterpret_cast<char*>(c_start.data()), sizeof(int32_t) * c_start.size());
+        in.read(reinterpret_cast<char*>(c_col.data()), sizeof(int32_t) * c_col.size());
+        in.read(reinterpret_cast<char*>(c_val.data()), (std::streamsize)c_val.size());
+        if (!in) throw std::runtime_error("truncated table cache " + ext_.table_cache);
+        csr = t2d_table_csr{hdr[1], c_start.data(), c_col.data(), c_val.data(), radius};
+        table.kind = item == 8 ? T2D_TABLE_CSR_F64 : (item == 4 ? T2D_TABLE_CSR_F32 : T2D_TABLE_CSR_U8);
+        table.data = &csr;
+    }
     t2d_params prm{};
     prm.v0 = v0;
     prm.k = k;

@@ -46,6 +46,8 @@ struct Extensions {
     bool quiet = false;                    // suppress the reference's per-step "Step: i" print
     int export_every = 1;                  // --export-every k: the Particle export / CSV of every k-th step only, fetched by
                                            // the asynchronous export (side stream + pinned ring) while the next k steps run
+    std::string table_cache;               // --table FILE: a T2DCSR1 binary cache of thresholded table rows (2dtissue_b200/table.py:
+                                           // hop counts or the metric geodesic variant) instead of building hop counts from the mesh
     bool device_seed = false;              // --device-seed: t2d_seed_particles (Philox on the GPU) instead of mt19937 on the host
 };
 

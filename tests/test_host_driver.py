@@ -146,3 +146,26 @@ def test_driver_export_every_k_async(sim, t2d, chart, tmp_path):
     r = subprocess.run([sim, "--mesh-path", CHART, "--particle-count", "300", "--step-count", "3", "--neigh", "euclid", "--sigma", "0.3",
                         "--device-seed", "--seed", "7", "--quiet", "--no-particles"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_driver_table_cache_geodesic(sim, t2d, chart, tmp_path):
+    """Row f4: `t2d_sim --table FILE` — the metric geodesic table as a T2DCSR1 binary cache (TableCSR.geodesic().save());
+    the driver's run equals the Python host fed the same rows."""
+    N, steps, sigma = 400, 5, 0.35
+    csr = t2d.TableCSR.geodesic(chart, 2.4 * sigma + 1e-9)
+    cache = str(tmp_path / "geo.t2dcsr")
+    csr.save(cache)
+    uv, n = t2d.seed_particles(N, seed=21)
+    s_in, s_out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    write_state(s_in, uv, n)
+    r = subprocess.run([sim, "--mesh-path", CHART, "--particle-count", str(N), "--step-count", str(steps), "--step-time", "0.02",
+                        "--neigh", "table", "--table", cache, "--sigma", repr(sigma), "--load-state", s_in, "--save-state", s_out,
+                        "--quiet", "--no-particles"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ctx = t2d.Context(chart, table=csr, v0=0.02, sigma=sigma, neigh_mode=t2d.NEIGH_TABLE, capacity=N)
+    ctx.set_particles(uv, n)
+    assert ctx.step(steps) == 0
+    ref = ctx.download()
+    uv2, n2, step = read_state(s_out)
+    assert step == steps and np.array_equal(uv2, ref["uv"]) and np.array_equal(n2, ref["n"])
