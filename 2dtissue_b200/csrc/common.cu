@@ -152,33 +152,47 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(int* __restrict__
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1) - ticket_base;
     __syncthreads();
     const int tile = s_tile;
+    // thread t owns the 16 consecutive buckets [base, base + 16) of the tile: a serial scan in registers, ONE block scan of the
+    // per-thread totals (the three-launch version chains four block scans per tile)
+    const int base = tile * SCAN_TILE + threadIdx.x * (SCAN_VEC * 4);
     int4 q[SCAN_VEC];
-    tile_load(count, M, tile, q);
+#pragma unroll
+    for (int k = 0; k < SCAN_VEC; ++k) {
+        const int b0 = base + 4 * k;
+        if (b0 + 3 < M) {
+            q[k] = *reinterpret_cast<const int4*>(count + b0);
+        } else {
+            int t[4] = {0, 0, 0, 0};
+            for (int j = 0; j < 4; ++j)
+                if (b0 + j < M) t[j] = count[b0 + j];
+            q[k] = make_int4(t[0], t[1], t[2], t[3]);
+        }
+    }
     int v = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_VEC; ++k) v += q[k].x + q[k].y + q[k].z + q[k].w;
     int total;
-    block_incl_scan(v, &total);
+    const int incl = block_incl_scan(v, &total);
     volatile unsigned long long* st = status;
     const unsigned long long tag = (unsigned long long)(seq & 0x3fffffffu) << 34;
     if (threadIdx.x == 0) st[tile] = tag | ((unsigned long long)(tile == 0 ? 2u : 1u) << 32) | (unsigned)total;
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         int excl = 0;
-        for (int base = tile - 1; base >= 0; base -= 32) {
-            const int idx = base - lane;
+        for (int lb = tile - 1; lb >= 0; lb -= 32) {
+            const int idx = lb - lane;
             unsigned long long w = tag | (2ull << 32);   // before the first tile: inclusive, value 0
             if (idx >= 0) {
                 do {
                     w = st[idx];
                 } while ((w >> 34) != (tag >> 34) || ((w >> 32) & 3u) == 0u);
             }
-            const unsigned incl = __ballot_sync(0xffffffffu, ((w >> 32) & 3u) == 2u);
-            const int last = incl ? __ffs(incl) - 1 : 31;   // nearest predecessor that already knows its inclusive prefix
+            const unsigned inclm = __ballot_sync(0xffffffffu, ((w >> 32) & 3u) == 2u);
+            const int last = inclm ? __ffs(inclm) - 1 : 31;   // nearest predecessor that already knows its inclusive prefix
             int val = lane <= last ? (int)(unsigned)w : 0;
             for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
             excl += __shfl_sync(0xffffffffu, val, 0);
-            if (incl) break;
+            if (inclm) break;
         }
         if (lane == 0) {
             s_prefix = excl;
@@ -186,32 +200,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(int* __restrict__
         }
     }
     __syncthreads();
-    int carry = s_prefix;
+    int run = s_prefix + incl - v;   // exclusive prefix of this thread's first bucket
 #pragma unroll
     for (int k = 0; k < SCAN_VEC; ++k) {
-        const int base = tile * SCAN_TILE + (k * SCAN_THREADS + threadIdx.x) * 4;
-        const int s = q[k].x + q[k].y + q[k].z + q[k].w;
-        int tot;
-        const int inc = block_incl_scan(s, &tot);
+        const int b0 = base + 4 * k;
         int4 o;
-        o.x = carry + inc - s;
+        o.x = run;
         o.y = o.x + q[k].x;
         o.z = o.y + q[k].y;
         o.w = o.z + q[k].z;
-        if (base + 3 < M) {
-            *reinterpret_cast<int4*>(start + base) = o;
-            *reinterpret_cast<int4*>(count + base) = make_int4(0, 0, 0, 0);
+        run = o.w + q[k].w;
+        if (b0 + 3 < M) {
+            *reinterpret_cast<int4*>(start + b0) = o;
+            *reinterpret_cast<int4*>(count + b0) = make_int4(0, 0, 0, 0);
         } else {
             const int t[4] = {o.x, o.y, o.z, o.w};
             for (int j = 0; j < 4; ++j)
-                if (base + j < M) {
-                    start[base + j] = t[j];
-                    count[base + j] = 0;
+                if (b0 + j < M) {
+                    start[b0 + j] = t[j];
+                    count[b0 + j] = 0;
                 }
         }
-        carry += tot;
     }
-    if (tile == nb - 1 && threadIdx.x == 0) start[M] = carry;
+    if (tile == nb - 1 && threadIdx.x == 0) start[M] = s_prefix + total;
 }
 
 void launch_scan_onepass(int* count, int* start, unsigned long long* status, int* ticket, int ticket_base, unsigned seq, int M,
