@@ -30,6 +30,9 @@ constexpr int F2_THREADS = 128;
 #ifndef T2D_F2_GRAB
 #define T2D_F2_GRAB 1   // consecutive 32-slot rows per queue ticket (measured: 1 -> 0.329 ms, 2 -> 0.362 ms, 4 -> 0.409 ms: the tail wins)
 #endif
+#ifndef T2D_F2_PACKED
+#define T2D_F2_PACKED 1   // 1: packed-fp32 candidate block (sm_100 FADD2 / FMUL2 / FFMA2; measured 0.343 -> 0.330 ms); 0: scalar fp32
+#endif
 #ifndef T2D_F2_UNROLL
 #define T2D_F2_UNROLL 4
 #endif
@@ -119,6 +122,50 @@ __device__ __forceinline__ void f2_candidate(const F2Rec& J, const float px, con
     // hand-scheduled PTX: 25 instructions per candidate, every value defined on every path (nothing for ptxas to spill or
     // to turn into branches); slot 361 = zero entry for "not in range", 362 = zero entry for "heading not in the table"
     float d2;
+#if T2D_F2_PACKED
+    // packed fp32 (sm_100 FADD2 / FMUL2 / FFMA2): (dx, dy), (ux, uy) and the force accumulation are one instruction each
+    asm("{\n\t"
+        ".reg .pred p, nz, c;\n\t"
+        ".reg .f32 dx2, dy2, dz, inv, g;\n\t"
+        ".reg .u32 idx, ad;\n\t"
+        ".reg .f64 tc, ts;\n\t"
+        ".reg .b64 pxy, jxy, dxy, sq, uxy, juv, gg, fxy;\n\t"
+        "mov.b64 pxy, {%8, %9};\n\t"
+        "mov.b64 jxy, {%11, %12};\n\t"
+        "sub.ftz.f32x2 dxy, pxy, jxy;\n\t"
+        "sub.ftz.f32 dz, %10, %13;\n\t"
+        "mul.ftz.f32x2 sq, dxy, dxy;\n\t"
+        "mov.b64 {dx2, dy2}, sq;\n\t"
+        "fma.rn.ftz.f32 %7, dz, dz, dx2;\n\t"
+        "add.ftz.f32 %7, %7, dy2;\n\t"
+        "setp.lt.ftz.f32 p, %7, %19;\n\t"
+        "setp.neu.ftz.f32 nz, %7, 0f00000000;\n\t"
+        "setp.le.and.ftz.f32 c, %7, %20, nz;\n\t"
+        "@c add.s32 %4, %4, 1;\n\t"
+        "@p add.s32 %5, %5, 1;\n\t"
+        "selp.u32 idx, %14, 361, p;\n\t"
+        "max.u32 %6, %6, idx;\n\t"
+        "shl.b32 ad, idx, 4;\n\t"
+        "add.u32 ad, ad, %23;\n\t"
+        "ld.shared.v2.f64 {tc, ts}, [ad];\n\t"
+        "rsqrt.approx.ftz.f32 inv, %7;\n\t"
+        "selp.f32 inv, inv, 0f447A0000, nz;\n\t"
+        "fma.rn.ftz.f32 g, inv, %21, %22;\n\t"
+        "selp.f32 g, g, 0f00000000, p;\n\t"
+        "mov.b64 uxy, {%17, %18};\n\t"
+        "mov.b64 juv, {%15, %16};\n\t"
+        "sub.ftz.f32x2 uxy, uxy, juv;\n\t"
+        "mov.b64 gg, {g, g};\n\t"
+        "mov.b64 fxy, {%0, %1};\n\t"
+        "fma.rn.ftz.f32x2 fxy, gg, uxy, fxy;\n\t"
+        "mov.b64 {%0, %1}, fxy;\n\t"
+        "add.f64 %2, %2, tc;\n\t"
+        "add.f64 %3, %3, ts;\n\t"
+        "}"
+        : "+f"(acc.fx), "+f"(acc.fy), "+d"(acc.mx), "+d"(acc.my), "+r"(acc.color), "+r"(acc.hits), "+r"(oobm), "=f"(d2)
+        : "f"(px), "f"(py), "f"(pz), "f"(J.x), "f"(J.y), "f"(J.z), "r"(J.slot), "f"(J.u), "f"(J.v), "f"(ui.x), "f"(ui.y),
+          "f"(k.r2s), "f"(k.r2c), "f"(k.g1), "f"(k.g0), "r"(s_trig));
+#else
     asm("{\n\t"
         ".reg .pred p, nz, c;\n\t"
         ".reg .f32 dx, dy, dz, inv, g, ux, uy;\n\t"
@@ -154,6 +201,7 @@ __device__ __forceinline__ void f2_candidate(const F2Rec& J, const float px, con
         : "+f"(acc.fx), "+f"(acc.fy), "+d"(acc.mx), "+d"(acc.my), "+r"(acc.color), "+r"(acc.hits), "+r"(oobm), "=f"(d2)
         : "f"(px), "f"(py), "f"(pz), "f"(J.x), "f"(J.y), "f"(J.z), "r"(J.slot), "f"(J.u), "f"(J.v), "f"(ui.x), "f"(ui.y),
           "f"(k.r2s), "f"(k.r2c), "f"(k.g1), "f"(k.g0), "r"(s_trig));
+#endif
     if (TIES) {
         const unsigned bm1 = __float_as_uint(d2) - 1u;
         if ((bm1 - k.tie_s_lo) <= 2u * F2_TIE_ULPS || (bm1 - k.tie_c_lo) <= 2u * F2_TIE_ULPS) acc.ties++;
