@@ -2,12 +2,16 @@
 //
 //   k_bin               bucket key of every resident particle + arrival rank + histogram (K1; after uploads only —
 //                       during stepping the producing kernel emits the next keys itself)
-//   k_scatter           counting-sort scatter of the SoA state into bucket order (K2); makes the fp32 path's cos/sin array
-//   k_step_euclid_fast  stages 2-5 FUSED for the Euclidean criterion, fp32: sparse row index of the cell list, 3 x 3 rows
-//                       of 3-cell x-runs, force + alignment (+ noise), Euler, seam re-entry, re-projection, next key
+//   k_scatter           counting-sort scatter of the SoA state into bucket order (K2); makes the 32-byte records of the fp32 path
+//   k_scatter_lean(_comm), k_expand   the lean sort of the fp32 fast path: record + aux + source index only; full state on demand
+//   k_build_nbr         setup: static neighbourhood table of the sparse row index (nine compact-cell runs per cell)
+//   (k_step_fast2       the benchmarked fp32 kernel, stages 2-5 FUSED for the Euclidean criterion: step_fast2.cuh)
+//   k_step_euclid_fast  the round-1 fp32 kernel (T2D_STEP=legacy): sparse row index of the cell list, 3 x 3 rows of 3-cell
+//                       x-runs, force + alignment (+ noise), Euler, seam re-entry, re-projection, next key
 //   k_step_euclid_exact the same, fp64 parity path: in-range neighbours summed in ascending global id
-//   k_neigh_table       stages 2-4a for the vertex-distance-table criterion: one CTA per bucket, neighbour
+//   k_neigh_table       stages 2-4a for the vertex-distance-table criterion, fp64: one CTA per bucket, neighbour
 //                       buckets from the thresholded CSR row, shared-memory staging, exact ascending-id sums (K3)
+//   k_neigh_table_warp  the same for fp32: one warp per bucket, coalesced neighbour loads broadcast by shuffles
 //   k_wrap_project      table mode: seam re-entry + UV point location + 3-D lift + validation + next key (K4+K5)
 //   k_comm_pack / k_comm_unpack / k_comm_unpack_far   slab exchange (multi-GPU): classify + pack, append what arrived
 //
@@ -601,10 +605,11 @@ __device__ __forceinline__ void slab_classify(const StepArgs<R>& a, const Partic
 //   k_step_euclid_exact  fp64 parity path: the in-range neighbours are gathered, sorted by global id and summed in
 //                        that order (the reference sums in ascending j), so forces are bit-identical; rows longer
 //                        than KMAX are ordered by repeated selection (still exact, counted).
-//   k_step_euclid_fast   fp32 fast path: predicates on squared distances, one rsqrt per in-range pair, sums in
-//                        visiting order, (cos, sin) of the neighbours' headings from the per-particle `cs` array,
-//                        UV point location deferred to a CTA-wide compacted pass for the particles that left
-//                        their previous face.
+//   k_step_euclid_fast   the round-1 fp32 kernel, kept behind T2D_STEP=legacy for A/B runs: predicates on squared
+//                        distances, one rsqrt per in-range pair (d = 0 -> 0.001 as a select), sums in visiting order,
+//                        (cos, sin) of the neighbours' headings from the per-particle `cs` array, point location per
+//                        thread (previous-face hint, else the grid cell's faces).  The benchmarked fp32 kernel is
+//                        k_step_fast2 (step_fast2.cuh); both share fast_epilogue() below.
 // ---------------------------------------------------------------------------------------------------
 constexpr int EUCLID_KMAX = 192;   // in-range neighbours ordered in the per-thread list (local memory); longer rows: repeated selection
 #ifndef T2D_STEP_THREADS
