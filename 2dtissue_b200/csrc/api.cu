@@ -12,6 +12,7 @@
 #include <emmintrin.h>
 #endif
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -261,6 +262,9 @@ template <typename R> class Engine : public EngineBase {
     long long export_step_[2] = {0, 0};
     unsigned export_seq_ = 0;
     // host-buffer path of fp32 contexts: float staging + widening on host threads, chunked so that it overlaps the transfers
+    DevBuf<int> d_inv_;             // caller index -> sorted slot (lean sorts write it while step_host32 runs)
+    DevBuf<int> d_face_hint_;       // face of every particle (caller order) when the last step_host32 returned
+    int face_hint_n_ = -1;          // particle count those hints belong to (-1: none)
     float* h32_ = nullptr;          // pinned: [5N] in (uv, r3d) followed by [7N] out (uv, r3d, rdot)
     size_t h32_cap_ = 0;            // particles the pinned staging holds
     cudaEvent_t ev_chunk_[16] = {};
@@ -1504,7 +1508,7 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
     }
     if (export_stream_) cudaStreamDestroy(export_stream_);
         h32_ = nullptr;
-        CK(cudaHostAlloc((void**)&h32_, sizeof(float) * 12 * (size_t)capacity_, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&h32_, sizeof(float) * 12 * (size_t)capacity_ + sizeof(DevCounters) + 64, cudaHostAllocDefault));
         h32_cap_ = (size_t)capacity_;
         for (auto& e : ev_chunk_)
             if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1521,6 +1525,10 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
     float* dout = (float*)d_stage_out_.p;                 // [7n] floats, then heading, vid, color
     int* dout_i = (int*)(dout + 7 * n);
     const int ncol_in = reproject ? 2 : 5;
+    const bool trace = getenv("T2D_HOST32_TRACE") != nullptr;   // dev: host-side timeline of the phases, microseconds
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_in = 0, t_enq = 0, t_first = 0;
     // ---- inputs: narrow a chunk on the host threads, put it on the bus, narrow the next one meanwhile ----
     for (int c = 0; c < K; ++c) {
         const size_t a = std::min(n, (size_t)c * cs), b = std::min(n, a + cs);
@@ -1533,35 +1541,67 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
                 for (size_t i = ta; i < tb; ++i) dst[i] = (float)src[i];
             }
         });
-        for (int col = 0; col < ncol_in; ++col)
-            CK(cudaMemcpyAsync(din + col * n + a, hin + col * n + a, sizeof(float) * (b - a), cudaMemcpyHostToDevice, stream_));
+        // the chunk of every column in ONE call: `ncol_in` rows of (b - a) floats, row pitch = one column
+        CK(cudaMemcpy2DAsync(din + a, sizeof(float) * n, hin + a, sizeof(float) * n, sizeof(float) * (b - a), (size_t)ncol_in,
+                             cudaMemcpyHostToDevice, stream_));
     }
     CK(cudaMemcpyAsync(din_i, heading, sizeof(int) * n, cudaMemcpyHostToDevice, stream_));
     if (!reproject) CK(cudaMemcpyAsync(din_i + n, vid, sizeof(int) * n, cudaMemcpyHostToDevice, stream_));
+    t_in = since();
     lean_ = false;
     this->N = N;
     A_.N = N;
-    HostViewIn32 in{din, din_i, reproject ? nullptr : din_i + n, reproject ? nullptr : din + 2 * n};
+    if (d_face_hint_.n < (size_t)capacity_) {
+        d_face_hint_.alloc((size_t)capacity_);
+        face_hint_n_ = -1;
+    }
+    // re-projection: the caller normally hands back the uv of the previous call, so every particle is still in the same face
+    HostViewIn32 in{din, din_i, reproject ? nullptr : din_i + n, reproject ? nullptr : din + 2 * n,
+                    (reproject && face_hint_n_ == N) ? d_face_hint_.p : nullptr};
     IoLaunch<R>::ingest32(N, in, A_.cur, stream_);
     launches_++;
     if (reproject) {
         Launch<R>::project_only(A_, stream_);
         launches_++;
     }
-    resort(false);
-    if (N > 0) one_step(true, nullptr, nullptr);
-    materialize();
-    HostViewOut32 o{dout, dout_i, dout_i + n, dout + 2 * n, dout + 5 * n, dout_i + 2 * n};
-    IoLaunch<R>::egest32(N, A_.cur, o, stream_);
-    launches_++;
+    HostViewOut32 o{dout, dout_i, dout_i + n, dout + 2 * n, dout + 5 * n, dout_i + 2 * n, d_face_hint_.p};
+    face_hint_n_ = N;
+    if (use_fast2_ && lean_ok_ && N > 0) {
+        // lean all the way: the upload is sorted straight into records (one full sector per particle instead of six partial
+        // ones — the particles arrive in caller order, so this sort is a random permutation), the step runs on them, and
+        // the export gathers by caller index through the inverse map the last sort left behind
+        if (d_inv_.n < (size_t)capacity_) d_inv_.alloc((size_t)capacity_);
+        Launch<R>::bin(A_, stream_);
+        scan_buckets();
+        A_.lean = 0;
+        A_.inv = nullptr;
+        Launch<R>::scatter_lean(A_, stream_);
+        std::swap(A_.cur, A_.alt);
+        launches_ += 2;
+        sorted_ = true;
+        lean_ = true;
+        A_.inv = d_inv_.p;
+        one_step(true, nullptr, nullptr);
+        A_.inv = nullptr;
+        IoLaunch<R>::egest32_lean(N, d_inv_.p, A_.src, A_.cur, A_.alt, o, stream_);
+        launches_++;
+    } else {
+        resort(false);
+        if (N > 0) one_step(true, nullptr, nullptr);
+        materialize();
+        IoLaunch<R>::egest32(N, A_.cur, o, stream_);
+        launches_++;
+    }
     // ---- outputs: chunk c of every array goes on the bus, an event marks it; the host widens chunk c while c+1 travels ----
-    DevCounters hc;
+    // the counters land in PINNED memory: a copy into pageable memory would block the host here until the whole step is done
+    DevCounters& hc = *reinterpret_cast<DevCounters*>(reinterpret_cast<unsigned char*>(h32_) + sizeof(float) * 12 * (size_t)capacity_ + 16);
+    hc.fault = 0;
     int nchunks = 0;
     for (int c = 0; c < K; ++c) {
         const size_t a = std::min(n, (size_t)c * cs), b = std::min(n, a + cs);
         if (a == b) break;
-        for (int col = 0; col < 7; ++col)
-            CK(cudaMemcpyAsync(hout + col * n + a, dout + col * n + a, sizeof(float) * (b - a), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpy2DAsync(hout + a, sizeof(float) * n, dout + a, sizeof(float) * n, sizeof(float) * (b - a), 7,
+                             cudaMemcpyDeviceToHost, stream_));   // 7 float columns of the chunk in one call
         CK(cudaMemcpyAsync(heading + a, dout_i + a, sizeof(int) * (b - a), cudaMemcpyDeviceToHost, stream_));
         CK(cudaMemcpyAsync(vid + a, dout_i + n + a, sizeof(int) * (b - a), cudaMemcpyDeviceToHost, stream_));
         CK(cudaMemcpyAsync(color + a, dout_i + 2 * n + a, sizeof(int) * (b - a), cudaMemcpyDeviceToHost, stream_));
@@ -1569,9 +1609,11 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
         CK(cudaEventRecord(ev_chunk_[c], stream_));
         nchunks++;
     }
+    t_enq = since();
     for (int c = 0; c < nchunks; ++c) {
         const size_t a = std::min(n, (size_t)c * cs), b = std::min(n, a + cs);
         CK(cudaEventSynchronize(ev_chunk_[c]));
+        if (c == 0) t_first = since();
         host_parallel(nt, [&](int t) {
             const size_t len = b - a, ta = a + len * t / nt, tb = a + len * (t + 1) / nt;
             for (int col = 0; col < 7; ++col) {
@@ -1589,6 +1631,9 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
     }
     CK(cudaStreamSynchronize(stream_));
     CK(cudaGetLastError());
+    if (trace)
+        fprintf(stderr, "t2d host32: inputs narrowed + enqueued %.0f us, everything enqueued %.0f us, first output chunk landed %.0f us, "
+                        "done %.0f us\n", t_in, t_enq, t_first, since());
     int fault = N > 0 ? (int)hc.fault : 0;
     if (fault) {
         unsigned zero = 0;

@@ -325,28 +325,33 @@ static __global__ void __launch_bounds__(256) k_scatter_lean(StepArgs<float> a)
     const int s = a.start[key] + (int)a.rank[i];
     a.alt.rec[2 * (size_t)s] = r0;
     a.alt.rec[2 * (size_t)s + 1] = r1;
-    a.alt.aux[s] = a.cur.aux[i];
+    const int4 ax = a.cur.aux[i];
+    a.alt.aux[s] = ax;
     a.src[s] = i;
+    if (a.inv) a.inv[ax.w] = s;   // host-buffer path: caller index -> slot, so that the export can gather instead of scatter
 }
 // The same in slab mode: the step kernel and the unpack kernels leave pos / uv / key in the pre-sort arrays (the slab
 // classification needs them), halo copies of the previous step and leavers carry KEY_DROP, and the resident count lives on
 // the device.  Still only record + aux + source index are written in bucket order.
-static __global__ void __launch_bounds__(256) k_scatter_lean_comm(StepArgs<float> a)
+// COMM = false: the same source format outside slab mode (right after an upload: pos / uv / key from k_ingest + k_bin).
+template <bool COMM> static __global__ void __launch_bounds__(256) k_scatter_lean_posuv(StepArgs<float> a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = a.comm.state->n_res;
-    if (i == 0) a.comm.state->n = a.start[a.M];   // residents after this sort (nobody reads n in this kernel)
+    const int n = COMM ? a.comm.state->n_res : a.N;
+    if (COMM && i == 0) a.comm.state->n = a.start[a.M];   // residents after this sort (nobody reads n in this kernel)
     if (i >= n) return;
     const uint32_t key = a.key[i];
-    if (key == KEY_DROP) return;
+    if (COMM && key == KEY_DROP) return;
     const int s = a.start[key] + (int)a.rank[i];
     const Pos3<float> P = a.cur.pos[i];
     const Real2<float> U = a.cur.uv[i];
     const int h = (int)P.w;
     a.alt.rec[2 * (size_t)s] = make_float4(P.x, P.y, P.z, __int_as_float((unsigned)h <= 360u ? h : 362));
     a.alt.rec[2 * (size_t)s + 1] = make_float4(U.x, U.y, __int_as_float((int)key), __int_as_float(h));
-    a.alt.aux[s] = a.cur.aux[i];
+    const int4 ax = a.cur.aux[i];
+    a.alt.aux[s] = ax;
     a.src[s] = i;
+    if (!COMM && a.inv) a.inv[ax.w] = s;
 }
 // the full sorted state from the lean one: pos / uv from the record, r_dot / colour through the source index
 // (a.alt = the pre-sort side that the last step kernel wrote)
@@ -1606,10 +1611,12 @@ template <typename R> __global__ void __launch_bounds__(128) k_project_only(Step
         Real2<R> p = a.cur.uv[i];
         int face, vid;
         Pos3<R> X;
-        project_point<R>(a.mesh, p.x, p.y, -1, face, vid, X, bc);
+        int4 ax = a.cur.aux[i];
+        // ax.y = -1 after an upload; the host-buffer path of fp32 contexts passes the face of the previous call as a hint
+        // (accepted only when the point is well inside it, otherwise the full search runs: same result either way)
+        project_point<R>(a.mesh, p.x, p.y, ax.y, face, vid, X, bc);
         X.w = a.cur.pos[i].w;
         a.cur.pos[i] = X;
-        int4 ax = a.cur.aux[i];
         ax.x = vid;
         ax.y = face;
         a.cur.aux[i] = ax;
@@ -1685,9 +1692,11 @@ template <typename R> void Launch<R>::scatter_lean(const StepArgs<R>& a, cudaStr
         const int n = launch_extent<R>(a);
         if (n <= 0) return;
         if (a.comm.on)
-            k_scatter_lean_comm<<<div_up(n, 256), 256, 0, s>>>(a);
+            k_scatter_lean_posuv<true><<<div_up(n, 256), 256, 0, s>>>(a);
+        else if (a.lean)
+            k_scatter_lean<<<div_up(n, 256), 256, 0, s>>>(a);           // source = records written by k_step_fast2
         else
-            k_scatter_lean<<<div_up(n, 256), 256, 0, s>>>(a);
+            k_scatter_lean_posuv<false><<<div_up(n, 256), 256, 0, s>>>(a);   // source = pos / uv / key (after an upload)
     }
 }
 template <typename R> void Launch<R>::expand(const StepArgs<R>& a, cudaStream_t s)

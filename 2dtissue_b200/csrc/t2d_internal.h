@@ -154,6 +154,7 @@ template <typename R> struct StepArgs {
     int* work_counter = nullptr;   // [4] dynamic queues: [0] buckets of the table-mode kernel, [1], [2] chunk queues of k_step_fast2
     const float4* rec_sentinel = nullptr;   // one record that is nobody's neighbour: what the masked tail trips of k_step_fast2 read
     int* src = nullptr;            // lean pipeline: sorted slot -> index in the pre-sort arrays (r_dot, colour)
+    int* inv = nullptr;            // host-buffer path: index in the caller's arrays -> sorted slot (written by the lean sorts when set)
     int lean = 0;                  // 1: k_step_fast2 writes records (alt.rec) instead of pos / uv / key (single context, fp32 Euclid)
     int ablate = 0;                // dev builds (-DT2D_F2_ABLATE) only: 1 no candidate loop, 2 no epilogue, 3 loads only
     int queue_flip = 0;            // which of the two chunk queues the next k_step_fast2 launch uses (it zeroes the other one)
