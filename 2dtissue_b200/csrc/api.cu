@@ -1120,6 +1120,9 @@ int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* c
     for (int d = 0; d < 2; ++d) {
         comm_send_[d].alloc(msg_bytes_);
         comm_recv_[d].alloc(msg_bytes_);
+        // the messages travel at their full fixed size: define the never-filled tails once (initcheck-clean transports)
+        CK(cudaMemsetAsync(comm_send_[d].p, 0, msg_bytes_, stream_));
+        CK(cudaMemsetAsync(comm_recv_[d].p, 0, msg_bytes_, stream_));
         CK(cudaMemsetAsync(comm_send_[d].p, 0, 16, stream_));
         CK(cudaMemsetAsync(comm_recv_[d].p, 0, 16, stream_));
         A_.comm.send[d] = comm_send_[d].p;
@@ -1133,6 +1136,8 @@ int Engine<R>::comm_init(int rank, int world, const uint8_t* id, const double* c
     far_bytes_ = Launch<R>::comm_far_bytes();
     far_send_.alloc(far_bytes_);
     far_recv_.alloc(far_bytes_ * (size_t)world);
+    CK(cudaMemsetAsync(far_send_.p, 0, far_bytes_, stream_));
+    CK(cudaMemsetAsync(far_recv_.p, 0, far_bytes_ * (size_t)world, stream_));
     CK(cudaMemsetAsync(far_send_.p, 0, 16, stream_));
     CK(cudaMemsetAsync(far_recv_.p, 0, far_bytes_ * (size_t)world, stream_));
     A_.comm.far_send = far_send_.p;
