@@ -1407,8 +1407,14 @@ int Engine<R>::step_host(int N, double* uv, int* heading, int* vid, double* r3d,
 {
     if (comm_on_) throw CudaError{"t2d_step_host is not available in slab mode"};
     {
-        const char* e = getenv("T2D_HOST32");   // dev knob: 0 = the plain path (doubles over PCIe, conversion on the device)
-        if (sizeof(R) == 4 && N >= 4096 && !(e && atoi(e) == 0)) return step_host32(N, uv, heading, vid, r3d, rdot, color, reproject);
+        // fp32 contexts: float staging + conversion on host threads (step_host32) — when this process has host cores for it.
+        // One process per GPU under torchrun: LOCAL_WORLD_SIZE ranks share the host's cores; below 4 cores per rank the plain
+        // path (doubles over PCIe, conversion on the device) is faster.  T2D_HOST32 = 0 / 1 forces either path.
+        const char* e = getenv("T2D_HOST32");
+        const char* lws = getenv("LOCAL_WORLD_SIZE");
+        const unsigned per_rank = std::thread::hardware_concurrency() / (unsigned)std::max(1, lws ? atoi(lws) : 1);
+        const bool want = e ? atoi(e) != 0 : per_rank >= 4;
+        if (sizeof(R) == 4 && N >= 4096 && want) return step_host32(N, uv, heading, vid, r3d, rdot, color, reproject);
     }
     if (reproject)
         set_state(N, uv, heading, nullptr, nullptr, nullptr, true);
@@ -1518,7 +1524,8 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
         for (auto& e : ev_chunk_)
             if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max(1, lws ? atoi(lws) : 1)));
     int K = 4;                                            // chunks per array (<= 16)
     if (const char* e = getenv("T2D_HOST32_T")) nt = std::max(1, std::min(64, atoi(e)));
     if (const char* e = getenv("T2D_HOST32_K")) K = std::max(1, std::min(16, atoi(e)));

@@ -435,9 +435,13 @@ def main_ours(args, rank, world, local_rank):
             ctx.step_host(h_uv, h_n, h_vid, h_r3d, h_rdot, h_col, reproject=True)
         barrier()
         e2e_s = time.perf_counter() - te
-        if spec["dtype"] == "f32":
+        lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        host32 = os.environ.get("T2D_HOST32")
+        host32 = (host32 != "0") if host32 is not None else (os.cpu_count() or 1) // max(1, lws) >= 4
+        if spec["dtype"] == "f32" and host32:
             # fp32 contexts: the caller's arrays are doubles in the reference's layouts, but the library narrows / widens them on
             # host threads (Engine::step_host32) and the PCIe bus carries floats: uv + heading up, uv, r3d, rdot + 3 int arrays down
+            # (only when the rank has >= 4 host cores to itself; otherwise doubles travel and the device converts)
             h2d = Nloc * (8 + 4)
             d2h = Nloc * (8 + 12 + 8 + 4 + 4 + 4)
         else:
