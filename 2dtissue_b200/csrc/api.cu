@@ -1531,7 +1531,7 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
     if (const char* e = getenv("T2D_HOST32_K")) K = std::max(1, std::min(16, atoi(e)));
     const size_t cs = ((n + K - 1) / K + 63) & ~(size_t)63;
     float* hin = h32_;                                    // [2n] uv, then [3n] r3d
-    float* hout = h32_ + 5 * (size_t)capacity_;           // [2n] uv, [3n] r3d, [2n] rdot
+    float* hout = h32_ + 5 * h32_cap_;                    // [2n] uv, [3n] r3d, [2n] rdot
     float* din = (float*)d_stage_in_.p;                   // device staging, same layout as hin + ints behind
     int* din_i = (int*)(din + 5 * n);                     // heading [n], vid [n]
     float* dout = (float*)d_stage_out_.p;                 // [7n] floats, then heading, vid, color
@@ -1606,7 +1606,7 @@ int Engine<R>::step_host32(int N, double* uv, int* heading, int* vid, double* r3
     }
     // ---- outputs: chunk c of every array goes on the bus, an event marks it; the host widens chunk c while c+1 travels ----
     // the counters land in PINNED memory: a copy into pageable memory would block the host here until the whole step is done
-    DevCounters& hc = *reinterpret_cast<DevCounters*>(reinterpret_cast<unsigned char*>(h32_) + sizeof(float) * 12 * (size_t)capacity_ + 16);
+    DevCounters& hc = *reinterpret_cast<DevCounters*>(reinterpret_cast<unsigned char*>(h32_) + sizeof(float) * 12 * h32_cap_ + 16);
     hc.fault = 0;
     int nchunks = 0;
     for (int c = 0; c < K; ++c) {
