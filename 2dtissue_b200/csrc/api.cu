@@ -1209,7 +1209,7 @@ template <typename R> void Engine<R>::comm_phase1()
     if (halo_valid_) {
         A_.step = (uint64_t)step_index;
         if (use_fast2_ && Launch<R>::step_fast2(A_, true, sm_count_, stream_))
-            A_.queue_flip ^= 1;
+            A_.queue_flip++;
         else
             Launch<R>::step_euclid(A_, true, stream_);   // cur -> alt; classifies + packs every particle it has just moved
         std::swap(A_.cur, A_.alt);
@@ -1308,7 +1308,7 @@ template <typename R> void Engine<R>::one_step(bool moving, cudaEvent_t* ev, int
         A_.lean = lean ? 1 : 0;
         bool ran_fast2 = false;
         if (use_fast2_ && Launch<R>::step_fast2(A_, moving, sm_count_, stream_)) {
-            A_.queue_flip ^= 1;
+            A_.queue_flip++;
             ran_fast2 = true;
         } else {
             materialize();

@@ -39,6 +39,11 @@ constexpr int F2_THREADS = 128;
 constexpr int F2_TRIG_N = 361;   // headings 0..360: what alignment produces (OrientationHelper.cpp:102-116); seam re-entry makes the rest
 constexpr unsigned F2_TIE_ULPS = 8;
 
+#ifdef T2D_F2_TIMELINE
+static __device__ unsigned long long g_f2_timeline[2 * 8192];   // dev builds: (start, end) ns of every warp of the last launch
+static __device__ unsigned g_f2_rowstat[4 * 131072];            // per row: start ns (relative, low 32 bits), duration ns, max lane trips, sum lane trips
+#endif
+
 struct alignas(128) F2Smem {
     double2 trig[F2_TRIG_N + 3];            // entries 361 and 362 are overwritten with (0, 0): see f2_candidate
     int rkey[NRANGE][F2_THREADS];           // per thread (column): ranges longest first, (length << 4) | row
@@ -301,18 +306,28 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
     const int ob = start[M], ol = start[M + 1] - ob;   // overflow bucket: normally empty
     unsigned npairs_w = 0, nties_w = 0, ncut_w = 0, fb_w = 0;
 
+#ifdef T2D_F2_TIMELINE
+    unsigned long long t_start;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
     int next = 0;
     if (lane == 0) next = atomicAdd(queue, 1);
     mbar_wait(&sm.bar, 0);   // the table has landed (every thread observes the barrier itself)
     if (tid < 2) sm.trig[F2_TRIG_N + tid] = make_double2(0.0, 0.0);
     __syncthreads();
     const uint32_t s_trig = smem_u32(sm.trig);
-
     for (;;) {
-        const int ticket = __shfl_sync(0xffffffffu, next, 0);
-        if (ticket >= ngrabs) break;
-        if (lane == 0) next = atomicAdd(queue, 1);   // in flight while this grab is processed
-        const int grab = ticket;
+        // The ticket was taken when the previous row's candidate loops ended, not a whole row ahead: rows differ a lot in
+        // cost (after 200 steps of the headline run a row's candidate trips spread from 3 to 330 around a mean of 50, and
+        // its duration follows them), and a ticket taken a row ahead sat behind that row — measured with per-row timers,
+        // the last rows of the queue started ~100 us after half the warps had run out of work.  Late binding: -10 %.
+        const int grab = __shfl_sync(0xffffffffu, next, 0);
+        if (grab >= ngrabs) break;
+#ifdef T2D_F2_TIMELINE
+        int lane_trips = 0;
+        unsigned long long t_row;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_row));
+#endif
 #pragma unroll 1
         for (int sub = 0; sub < T2D_F2_GRAB; ++sub) {
             const int i = (grab * T2D_F2_GRAB + sub) * 32 + lane;
@@ -388,6 +403,9 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
                 for (int m = 0; m < 9; ++m) {
                     sm.rkey[m][tid] = key[m];
                     nr += key[m] >= 16 ? 1 : 0;
+#ifdef T2D_F2_TIMELINE
+                    lane_trips += ((key[m] >> 4) + T2D_F2_UNROLL - 1) / T2D_F2_UNROLL;
+#endif
                 }
 #ifdef T2D_F2_ABLATE
                 if (a.ablate == 1 || a.ablate == 4) nr = 0;   // dev: no candidate loop
@@ -430,6 +448,7 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
             }
 #endif
             __syncwarp();   // reconverge: lanes leave the candidate loops at different times, the tail is the same for all
+            if (sub == T2D_F2_GRAB - 1 && lane == 0) next = atomicAdd(queue, 1);   // next ticket: in flight during the epilogue
             unsigned npairs = 0, nties = 0;
             if (live) {
                 double2 own;
@@ -466,7 +485,29 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
             nties_w += nties;
             ncut_w += acc.ties;
         }
+#ifdef T2D_F2_TIMELINE
+        {
+            __syncwarp();
+            const int mx = __reduce_max_sync(0xffffffffu, lane_trips), sm_ = __reduce_add_sync(0xffffffffu, lane_trips);
+            unsigned long long t_row_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_row_end));
+            if (lane == 0 && grab < 131072) {
+                g_f2_rowstat[4 * grab] = (unsigned)t_row;
+                g_f2_rowstat[4 * grab + 1] = (unsigned)(t_row_end - t_row);
+                g_f2_rowstat[4 * grab + 2] = (unsigned)mx;
+                g_f2_rowstat[4 * grab + 3] = (unsigned)sm_;
+            }
+        }
+#endif
     }
+#ifdef T2D_F2_TIMELINE
+    if (lane == 0) {   // dev: per-warp timeline (start, end in ns)
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        const int gw = blockIdx.x * (F2_THREADS / 32) + (tid >> 5);
+        if (gw < 8192) { g_f2_timeline[2 * gw] = t_start; g_f2_timeline[2 * gw + 1] = t_end; }
+    }
+#endif
     // diagnostic counters: one atomic per warp and counter
     npairs_w = __reduce_add_sync(0xffffffffu, npairs_w);
     nties_w = __reduce_add_sync(0xffffffffu, nties_w);
@@ -490,7 +531,7 @@ template <typename R> bool Launch<R>::step_fast2(const StepArgs<R>& a, bool movi
         int grid = sm_count * T2D_F2_MIN_BLOCKS;
         if (grid > div_up(ngrabs, F2_THREADS / 32)) grid = div_up(ngrabs, F2_THREADS / 32);
         int* q0 = a.work_counter + 1 + (a.queue_flip & 1);   // two queue counters, used alternately: every launch zeroes the
-        int* q1 = a.work_counter + 1 + ((a.queue_flip + 1) & 1);   // other one (the caller flips queue_flip after each launch)
+        int* q1 = a.work_counter + 1 + ((a.queue_flip + 1) & 1);   // other one (the caller advances queue_flip after each launch)
         if (moving) {
             if (a.count_ties)
                 k_step_fast2<true, true><<<grid, F2_THREADS, 0, s>>>(a, q0, q1);

@@ -157,7 +157,7 @@ template <typename R> struct StepArgs {
     int* inv = nullptr;            // host-buffer path: index in the caller's arrays -> sorted slot (written by the lean sorts when set)
     int lean = 0;                  // 1: k_step_fast2 writes records (alt.rec) instead of pos / uv / key (single context, fp32 Euclid)
     int ablate = 0;                // dev builds (-DT2D_F2_ABLATE) only: 1 no candidate loop, 2 no epilogue, 3 loads only
-    int queue_flip = 0;            // which of the two chunk queues the next k_step_fast2 launch uses (it zeroes the other one)
+    int queue_flip = 0;            // launch number of k_step_fast2: its low bit picks the queue counter (the launch zeroes the other one)
 };
 
 // kernel launchers implemented once per precision (step_f64.cu with --fmad=false, step_f32.cu with FMA)
