@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
         // the last rows of the queue started ~100 us after half the warps had run out of work.  Late binding: -10 %.
         const int grab = __shfl_sync(0xffffffffu, next, 0);
         if (grab >= ngrabs) break;
-#ifdef T2D_F2_TIMELINE
+#if defined(T2D_F2_TIMELINE) && T2D_F2_TIMELINE == 1   // per-row timers (heavier than the per-warp ones)
         int lane_trips = 0;
         unsigned long long t_row;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_row));
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
                 for (int m = 0; m < 9; ++m) {
                     sm.rkey[m][tid] = key[m];
                     nr += key[m] >= 16 ? 1 : 0;
-#ifdef T2D_F2_TIMELINE
+#if defined(T2D_F2_TIMELINE) && T2D_F2_TIMELINE == 1   // per-row timers (heavier than the per-warp ones)
                     lane_trips += ((key[m] >> 4) + T2D_F2_UNROLL - 1) / T2D_F2_UNROLL;
 #endif
                 }
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
             nties_w += nties;
             ncut_w += acc.ties;
         }
-#ifdef T2D_F2_TIMELINE
+#if defined(T2D_F2_TIMELINE) && T2D_F2_TIMELINE == 1   // per-row timers (heavier than the per-warp ones)
         {
             __syncwarp();
             const int mx = __reduce_max_sync(0xffffffffu, lane_trips), sm_ = __reduce_add_sync(0xffffffffu, lane_trips);

@@ -52,6 +52,8 @@ for rep in range(3):
     # per SM last end: block b -> 4 warps; SM unknown, use block
     ends = np.sort(en)[::-1]
     print("  last 10 ends", ends[:10].round(1), " 100th", ends[100].round(1), "1000th", ends[1000].round(1))
+    if len(sys.argv) > 3 and sys.argv[3] == "warps":
+        continue
     L.t2d_dev_rowstat(rs.ctypes.data_as(C.POINTER(C.c_uint)))
     R = rs.reshape(-1, 4).astype(np.int64)
     R = R[R[:, 1] > 0]
