@@ -616,7 +616,13 @@ __device__ __forceinline__ void slab_classify(const StepArgs<R>& a, const Partic
 //                        thread (previous-face hint, else the grid cell's faces).  The benchmarked fp32 kernel is
 //                        k_step_fast2 (step_fast2.cuh); both share fast_epilogue() below.
 // ---------------------------------------------------------------------------------------------------
-constexpr int EUCLID_KMAX = 192;   // in-range neighbours ordered in the per-thread list (local memory); longer rows: repeated selection
+#ifndef T2D_EUCLID_KMAX
+#define T2D_EUCLID_KMAX 1024
+#endif
+// in-range neighbours ordered in the per-thread list (local memory; only the entries in use are touched); longer rows: repeated
+// selection, O(row x candidates).  192 in round 1: inside the clumps the lift produces, rows of 200-600 are common after a few
+// tens of steps, and the selection path then took ~45 % of the kernel's stall samples at 6 of 32 lanes (ncu source page)
+constexpr int EUCLID_KMAX = T2D_EUCLID_KMAX;
 #ifndef T2D_STEP_THREADS
 #define T2D_STEP_THREADS 128
 #endif
@@ -702,10 +708,11 @@ template <typename R, bool MOVING> __global__ void __launch_bounds__(STEP_THREAD
         if (!overflow) {
             // Shell sort by (id, slot), Ciura gaps: ~k^1.3 moves instead of k^2/4 — rows of 50-200 neighbours are
             // common inside the clumps the lift produces (ncu: the plain insertion sort was 31 % of the kernel)
-            const int gaps[6] = {132, 57, 23, 10, 4, 1};
+            const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
 #pragma unroll 1
-            for (int gi = 0; gi < 6; ++gi) {
+            for (int gi = 0; gi < 8; ++gi) {
                 const int gap = gaps[gi];
+                if (gap >= cnt) continue;
                 for (int p = gap; p < cnt; ++p) {
                     unsigned long long kx = list[p];
                     int q = p - gap;

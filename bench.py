@@ -378,7 +378,8 @@ def main_ours(args, rank, world, local_rank):
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.counters()["kernel_launches"]
+    timed_counters = ctx.counters()
+    launches = timed_counters["kernel_launches"]
     if fault:
         sys.stderr.write("rank %d: simulation fault mask %d during the timed steps (1 lost, 2 non-finite, 4 wrap cap, "
                          "8 migration, 16 message overflow): the measurement is invalid\n" % (rank, fault))
@@ -503,6 +504,7 @@ def main_ours(args, rank, world, local_rank):
                                "(2/3/3/4 levels at 1/2/4/8 GPUs) and sigma follows the total particle count, so the per-GPU work "
                                "is similar, not identical, along the curve"} if args.workload == "c4shard" else {})},
                 "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
+                "counters": {k: int(timed_counters[k]) for k in ("pairs_in_range", "max_row", "order_fallbacks", "ties_cutoff", "wraps", "locate_fallbacks")},
                 **({"transport_parity": parity} if parity is not None else {}),
                 "kernel_ms": prof, "roofline": roof,
                 "cpu_baseline": cb,
