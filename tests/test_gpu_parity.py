@@ -209,7 +209,7 @@ def test_step_fp32_fast_path(t2d, chart, hop_table, metric_tab, name):
 # ------------------------------------------------------------------------------------------------------
 # fresh seeded inputs against the oracle, larger N
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode,N,sigma", [(1, 30000, None), (0, 20000, 0.4166666666666667), (0, 6000, 1.3)])
+@pytest.mark.parametrize("mode,N,sigma", [(1, 30000, None), (0, 20000, 0.4166666666666667), (0, 6000, 1.3), (1, 15000, 0.9)])
 def test_step_vs_oracle_seeded(t2d, chart, oracle, hop_table, mode, N, sigma):
     uv, n = t2d.seed_particles(N, seed=77 + N)
     if sigma is None:
@@ -239,6 +239,10 @@ def test_step_vs_oracle_seeded(t2d, chart, oracle, hop_table, mode, N, sigma):
         uv_c, n_c, vid_c, r3d_c = o["uv"], o["n"], o["vid"], o["r3d"]
     c = ctx.counters()
     assert c["pairs_in_range"] > 0 and c["cell_fallbacks"] == 0   # order_fallbacks = rows summed by selection: still exact
+    if mode == 1 and sigma > 0.5:
+        # dense Euclid case: rows beyond the ordered list of the exact kernel (1024 entries) take the repeated-selection
+        # path, shorter ones the long Shell-sort gaps — both must stay bit-exact
+        assert c["max_row"] > 1024 and c["order_fallbacks"] > 0, c
 
 
 def test_noise_parity_with_oracle(t2d, chart, oracle):
