@@ -410,6 +410,7 @@ template <typename R> Engine<R>::Engine(const t2d_mesh* mesh, const t2d_table* t
         A_.rec_sentinel = d_rec_sentinel_.p;
         d_src_.alloc(C);
         A_.src = d_src_.p;
+        if (const char* pe = getenv("T2D_PDL")) A_.pdl = atoi(pe) != 0;
         const char* le = getenv("T2D_LEAN");
         lean_ok_ = !(le && atoi(le) == 0);
     }
@@ -710,7 +711,7 @@ template <typename R> void Engine<R>::scan_buckets()
         CK(cudaMemsetAsync(d_work_.p + 3, 0, sizeof(int), stream_));
         scan_ticket_base_ = 0;
     }
-    launch_scan_onepass(A_.count, A_.start, d_scan_status_.p, d_work_.p + 3, scan_ticket_base_, ++scan_seq_, A_.M, stream_);
+    launch_scan_onepass(A_.count, A_.start, d_scan_status_.p, d_work_.p + 3, scan_ticket_base_, ++scan_seq_, A_.M, stream_, A_.pdl != 0);
     scan_ticket_base_ += nb;
     launches_++;
 }

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(int* __restrict__
                                                                int M, int nb)
 {
     __shared__ int s_tile, s_prefix;
+    pdl_wait();
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1) - ticket_base;
     __syncthreads();
     const int tile = s_tile;
@@ -226,10 +227,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(int* __restrict__
 }
 
 void launch_scan_onepass(int* count, int* start, unsigned long long* status, int* ticket, int ticket_base, unsigned seq, int M,
-                         cudaStream_t s)
+                         cudaStream_t s, bool pdl)
 {
     const int nb = scan_blocks(M);
-    if (nb > 0) k_scan_onepass<<<nb, SCAN_THREADS, 0, s>>>(count, start, status, ticket, ticket_base, seq, M, nb);
+    if (nb > 0) launch_pdl(pdl, k_scan_onepass, (unsigned)nb, (unsigned)SCAN_THREADS, s, count, start, status, ticket, ticket_base, seq, M, nb);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -318,6 +318,7 @@ template <typename R> __global__ void __launch_bounds__(256) k_scatter(StepArgs<
 // 4-byte source index through which k_expand finds r_dot / colour when a caller asks for them.
 static __global__ void __launch_bounds__(256) k_scatter_lean(StepArgs<float> a)
 {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     const float4 r0 = a.cur.rec[2 * (size_t)i], r1 = a.cur.rec[2 * (size_t)i + 1];
@@ -1701,7 +1702,7 @@ template <typename R> void Launch<R>::scatter_lean(const StepArgs<R>& a, cudaStr
         if (a.comm.on)
             k_scatter_lean_posuv<true><<<div_up(n, 256), 256, 0, s>>>(a);
         else if (a.lean)
-            k_scatter_lean<<<div_up(n, 256), 256, 0, s>>>(a);           // source = records written by k_step_fast2
+            launch_pdl(a.pdl != 0, k_scatter_lean, (unsigned)div_up(n, 256), 256u, s, a);   // source = records written by k_step_fast2
         else
             k_scatter_lean_posuv<false><<<div_up(n, 256), 256, 0, s>>>(a);   // source = pos / uv / key (after an upload)
     }

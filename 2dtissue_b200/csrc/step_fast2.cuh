@@ -279,7 +279,6 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
     if (tid == 0) {
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (blockIdx.x == 0) *queue_next = 0;   // the queue of the NEXT launch (launches alternate between two counters)
     }
     __syncthreads();
     if (tid == 0) {    // cos/sin of 0..360 degrees as the host's libm gives them: one bulk copy per CTA
@@ -297,6 +296,8 @@ __global__ void __launch_bounds__(F2_THREADS, T2D_F2_MIN_BLOCKS) k_step_fast2(St
         k.tie_s_lo = __float_as_uint(k.r2s) - F2_TIE_ULPS - 1u;
         k.tie_c_lo = __float_as_uint(k.r2c) - F2_TIE_ULPS - 1u;
     }
+    pdl_wait();   // everything above touches only constants and this CTA's shared memory (programmatic dependent launch)
+    if (blockIdx.x == 0 && tid == 0) *queue_next = 0;   // the queue of the NEXT launch (launches alternate between two counters)
     const int nres = resident_count<R>(a);
     const int ngrabs = (nres + 32 * T2D_F2_GRAB - 1) / (32 * T2D_F2_GRAB);
     const int M = a.vox.M;
@@ -534,11 +535,11 @@ template <typename R> bool Launch<R>::step_fast2(const StepArgs<R>& a, bool movi
         int* q1 = a.work_counter + 1 + ((a.queue_flip + 1) & 1);   // other one (the caller advances queue_flip after each launch)
         if (moving) {
             if (a.count_ties)
-                k_step_fast2<true, true><<<grid, F2_THREADS, 0, s>>>(a, q0, q1);
+                launch_pdl(a.pdl != 0, k_step_fast2<true, true>, grid, F2_THREADS, s, a, q0, q1);
             else
-                k_step_fast2<true, false><<<grid, F2_THREADS, 0, s>>>(a, q0, q1);
+                launch_pdl(a.pdl != 0, k_step_fast2<true, false>, grid, F2_THREADS, s, a, q0, q1);
         } else {
-            k_step_fast2<false, true><<<grid, F2_THREADS, 0, s>>>(a, q0, q1);
+            launch_pdl(a.pdl != 0, k_step_fast2<false, true>, grid, F2_THREADS, s, a, q0, q1);
         }
         return true;
     } else {
