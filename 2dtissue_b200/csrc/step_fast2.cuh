@@ -9,15 +9,17 @@
 // Same arithmetic as the round-1 kernel (k_step_euclid_fast, kept behind T2D_STEP=legacy); what changed is where the
 // instructions and the waiting went (ncu, profiles/r01_step_fast_lines.md: 17 % of the kernel's instructions found the nine
 // candidate ranges, 18 % of its stall samples waited for the cs[j] gather, issue slots 53 % busy):
-//   * ONE 32-byte record per candidate {x, y, z, heading | u, v, cell, -} (made by the counting-sort scatter): the distance
+//   * ONE 32-byte record per candidate {x, y, z, trig slot | u, v, cell, heading} (made by the counting-sort scatter): the distance
 //     test reads the first half, an in-range pair the second half of the SAME sector — no second and third gather;
 //   * (cos n, sin n) of a neighbour's heading comes from a 361-entry copy of the host-libm table in shared memory, loaded
 //     once per CTA by the TMA unit (cp.async.bulk + mbarrier); the 16-byte-per-particle cs array no longer exists;
 //   * the nine candidate ranges of a particle are two loads each from the STATIC neighbourhood table of its cell
 //     (t2d_internal.h NBR_STRIDE) instead of a word lookup, two popcounts and bounds logic per row; the ranges are ordered
 //     longest-first by a sorting network on packed 32-bit keys (2 instructions per compare-exchange);
-//   * persistent CTAs, warps independent of each other (no CTA barrier after the table load): every warp pulls runs of
-//     consecutive 32-slot chunks from a device-side queue.
+//   * persistent CTAs, warps independent of each other (no CTA barrier after the table load): every warp pulls one 32-slot
+//     row per ticket from a device-side queue, and takes the next ticket only when its candidate loops have ended (rows
+//     differ ~100x in cost; a ticket taken a row ahead waited behind that row);
+//   * launched with programmatic stream serialisation: the prologue up to pdl_wait() overlaps the tail of the scatter.
 #pragma once
 #include "kernels.cuh"
 
