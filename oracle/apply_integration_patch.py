@@ -14,7 +14,6 @@ The anchors are function names and member names of the reference; the inserted t
 usage: apply_integration_patch.py REF_DIR OUT_DIR
 """
 import os
-import re
 import sys
 
 ref, out = sys.argv[1], sys.argv[2]

@@ -1,5 +1,4 @@
 """The C-ABI library loads (no GPU needed) and exports every symbol include/t2d.h declares."""
-import ctypes
 import importlib
 import os
 import re

@@ -60,7 +60,6 @@ def test_philox_matches_oracle(hd_lib, oracle_mod):
         assert a == b and 0.0 <= a < 1.0
         assert hd_lib.hd_noise_deg(0.3 * 360.0, seed, step, pid) == L.t2do_noise_deg(0.3, seed, step, pid)
     # Philox4x32-10 known answer (Random123 kat_vectors: counter 0, key 0)
-    import struct
     u = hd_lib.hd_philox_uniform(0, 0, 0)
     bits = int(u * 2 ** 53)
     assert bits == ((0x6627e8d5 << 32) | 0xe169c58d) >> 11

@@ -1,5 +1,5 @@
 """dev: local slab group (loopback transport) on the refined chart, fp32, to reproduce multi-GPU bench faults on one GPU"""
-import importlib, os, sys, time
+import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
