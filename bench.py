@@ -399,6 +399,12 @@ def main_ours(args, rank, world, local_rank):
         for name, ms in ctx.profile_step():
             prof.setdefault(name, []).append(ms)
     prof = {k: statistics.median(v) for k, v in prof.items()}
+    by_rank = None
+    if slabs:   # what every rank saw (kernel_ms above is rank 0's): the step is as slow as the slowest slab
+        row = {"rank": rank, "owned": int(ctx.owned_count()), "step_fused_ms": prof.get("step_fused"),
+               "exchange_unpack_ms": prof.get("exchange_unpack")}
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, row)
 
     phase = None
     if replicas:   # the phase diagram: relax every replica further (untimed), then read the polar order parameter
@@ -506,7 +512,7 @@ def main_ours(args, rank, world, local_rank):
                 "clocks": clocks, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                 "counters": {k: int(timed_counters[k]) for k in ("pairs_in_range", "max_row", "order_fallbacks", "ties_cutoff", "wraps", "locate_fallbacks")},
                 **({"transport_parity": parity} if parity is not None else {}),
-                "kernel_ms": prof, "roofline": roof,
+                "kernel_ms": prof, **({"by_rank": by_rank} if by_rank else {}), "roofline": roof,
                 "cpu_baseline": cb,
                 "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d * world),
                         "d2h_bytes_per_step": int(d2h * world), "steps": e2e_steps}}
